@@ -1,0 +1,85 @@
+// Shared device/host helpers for the hdiff_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define HD_OK 0
+#define HD_ERR_ARG (-1)       // bad shape / alignment / null pointer
+#define HD_ERR_UNSUPPORTED (-2)  // shape outside what this kernel family covers
+#define HD_ERR_CUDA (-3)      // launch failed (cudaGetLastError)
+#define HD_ERR_DRIVER (-4)    // driver entry point (tensor map encode) unavailable
+
+#define HD_F32 0
+#define HD_BF16 1
+
+#define HD_CHECK_LAUNCH() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { hd_set_error(cudaGetErrorString(e_)); return HD_ERR_CUDA; } } while (0)
+#define HD_REQUIRE(cond) do { if (!(cond)) { hd_set_error("requirement failed: " #cond); return HD_ERR_ARG; } } while (0)
+
+void hd_set_error(const char* msg);
+
+// ---------------------------------------------------------------------------------------------
+// Logical tensor views.  Every activation is physically NHWC [N][PH][PW][C].  A view with
+// P == 2 exposes the 2x2 space-to-depth rearrangement of that tensor as a logical
+// [N][H][W][4C] tensor (H = PH/2, W = PW/2, logical channel j = (py*2+px)*C + c).  Strided
+// convolutions and the transposed convolution become stride-1 convolutions on such views
+// ("views").
+// ---------------------------------------------------------------------------------------------
+struct HdView {
+    const void* p;   // base pointer (T)
+    int C;           // physical channels
+    int P;           // 1 or 2
+};
+
+__host__ __device__ __forceinline__ int64_t hd_view_off(int C, int P, int H, int W, int n, int y, int x, int j) {
+    // element offset of logical (n, y, x, j) inside the physical tensor
+    if (P == 1) return (((int64_t)n * H + y) * W + x) * C + j;
+    int q = j / C, c = j - q * C;
+    int py = q >> 1, px = q & 1;
+    return (((int64_t)n * (2 * H) + (2 * y + py)) * (2 * W) + (2 * x + px)) * C + c;
+}
+
+template <typename T> __device__ __forceinline__ float hd_ld(const T* p);
+template <> __device__ __forceinline__ float hd_ld<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float hd_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void hd_st(T* p, float v);
+template <> __device__ __forceinline__ void hd_st<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void hd_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float hd_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float hd_swish(float x) { return x * hd_sigmoid(x); }
+__device__ __forceinline__ float hd_swish_grad(float x) { float s = hd_sigmoid(x); return s * (1.f + x * (1.f - s)); }
+
+// Counter-based RNG for dropout: one 32-bit draw per (seed, element index); the backward pass
+// regenerates the mask from the same (seed, index) instead of storing it.
+__host__ __device__ __forceinline__ uint32_t hd_hash_u32(uint64_t seed, uint64_t idx) {
+    uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+__host__ __device__ __forceinline__ float hd_dropout_scale(uint64_t seed, uint64_t idx, float p_drop) {
+    // returns 0 (dropped) or 1/(1-p)
+    if (p_drop <= 0.f) return 1.f;
+    uint32_t r = hd_hash_u32(seed, idx);
+    float u = (float)(r >> 8) * (1.f / 16777216.f);
+    return u < p_drop ? 0.f : 1.f / (1.f - p_drop);
+}
+
+__device__ __forceinline__ float hd_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float hd_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+static inline int hd_num_sms() {
+    static int n = 0;
+    if (n == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}

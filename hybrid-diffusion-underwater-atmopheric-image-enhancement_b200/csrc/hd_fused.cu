@@ -1,0 +1,530 @@
+// HBM-bound fused kernels of the hdiff_b200 hot path (vectorised 16-byte accesses, warp/shared
+// reductions, no re-reads beyond the algorithmic minimum):
+//   K4  GroupNorm statistics / GroupNorm-apply + Swish (+ dropout) forward and backward
+//       (reference: nn.GroupNorm + Swish + nn.Dropout, DiffusionFreeGuidence/ModelCondition.py:128-129,141-143,95,249-250)
+//   K6  q_sample and noise-MSE forward/backward (DiffusionCondition.py:43-45)
+//   K7  CFG mix + posterior mean + noise step (+ NaN flag, final clip) (DiffusionCondition.py:74-80,91-98)
+//   colsum (bias / embedding-add gradients), fused global-norm clip + AdamW on the flat buffers
+//       (TrainCondition.py:61-63).
+#include "hd_common.cuh"
+
+template <typename T> struct Vec;
+template <> struct Vec<float> { static constexpr int N = 4; using raw = float4; };
+template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; using raw = uint4; };
+
+template <typename T> __device__ __forceinline__ void vec_load(const T* p, float* v);
+template <> __device__ __forceinline__ void vec_load<float>(const float* p, float* v) {
+    float4 r = *reinterpret_cast<const float4*>(p); v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+template <> __device__ __forceinline__ void vec_load<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <typename T> __device__ __forceinline__ void vec_store(T* p, const float* v);
+template <> __device__ __forceinline__ void vec_store<float>(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void vec_store<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+    uint4 r; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+}
+
+// Common description of a (possibly two-source) NHWC tensor [N][HW][C0 + C1].
+template <typename T>
+struct Src2 {
+    const T* p0; const T* p1; int C0, C1;
+    __device__ __forceinline__ const T* at(int n, int64_t pix, int64_t HW, int c) const {
+        return c < C0 ? p0 + ((int64_t)n * HW + pix) * C0 + c : p1 + ((int64_t)n * HW + pix) * C1 + (c - C0);
+    }
+};
+
+struct GnParams {
+    int N; int64_t HW; int C, G;
+    const double* sums;       // [N][G][2] (sum, sum of squares)
+    const float* gamma; const float* beta; float eps;
+    int act; float p_drop; uint64_t seed;
+};
+
+__device__ __forceinline__ void gn_load_stats(const GnParams& g, int n, float* s_mean, float* s_rstd) {
+    const double cnt = (double)(g.C / g.G) * (double)g.HW;
+    for (int i = threadIdx.x; i < g.G; i += blockDim.x) {
+        double s = g.sums[((int64_t)n * g.G + i) * 2], ss = g.sums[((int64_t)n * g.G + i) * 2 + 1];
+        double m = s / cnt, var = ss / cnt - m * m;
+        if (var < 0) var = 0;
+        s_mean[i] = (float)m; s_rstd[i] = (float)(1.0 / sqrt(var + (double)g.eps));
+    }
+}
+
+// ------------------------------- statistics -------------------------------------------------
+// grid (chunks, N).  thread <-> fixed channel vector, strides over the pixels of the chunk.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(Src2<T> x, int N, int64_t HW, int C, int G, int64_t pix_per_block, double* sums) {
+    constexpr int V = Vec<T>::N;
+    __shared__ float sg[64][2];
+    const int lanes = C / V, cpg = C / G;
+    const int ppi = blockDim.x / lanes;           // pixels per iteration
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) { sg[i][0] = 0.f; sg[i][1] = 0.f; }
+    __syncthreads();
+    const int lane = threadIdx.x % lanes, sub = threadIdx.x / lanes;
+    float s[V], ss[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+    if (sub < ppi) {
+        const int64_t p0 = blockIdx.x * pix_per_block;
+        const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
+        for (int64_t p = p0 + sub; p < p1; p += ppi) {
+            float v[V]; vec_load(x.at(n, p, HW, lane * V), v);
+#pragma unroll
+            for (int i = 0; i < V; ++i) { s[i] += v[i]; ss[i] += v[i] * v[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) { int g = (lane * V + i) / cpg; atomicAdd(&sg[g][0], s[i]); atomicAdd(&sg[g][1], ss[i]); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        atomicAdd(sums + ((int64_t)n * G + i) * 2, (double)sg[i][0]);
+        atomicAdd(sums + ((int64_t)n * G + i) * 2 + 1, (double)sg[i][1]);
+    }
+}
+
+static inline int64_t pick_chunk(int N, int64_t HW, int ppi, int* chunks_out) {
+    int64_t target_blocks = (int64_t)hd_num_sms() * 8;
+    int64_t chunks = (target_blocks + N - 1) / N;
+    int64_t max_chunks = (HW + ppi - 1) / ppi;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    int64_t ppb = (HW + chunks - 1) / chunks;
+    ppb = (ppb + ppi - 1) / ppi * ppi;
+    chunks = (HW + ppb - 1) / ppb;
+    *chunks_out = (int)chunks;
+    return ppb;
+}
+
+template <typename T>
+static int gn_check(int C0, int C1, int G) {
+    constexpr int V = Vec<T>::N;
+    int C = C0 + C1;
+    if (C % G != 0 || G > 64 || C % V != 0 || C0 % V != 0 || C / V > 256) { hd_set_error("groupnorm: unsupported channel configuration"); return HD_ERR_UNSUPPORTED; }
+    return HD_OK;
+}
+
+template <typename T>
+static int gn_stats_t(const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, double* sums, cudaStream_t st) {
+    int rc = gn_check<T>(C0, C1, G); if (rc) return rc;
+    int C = C0 + C1;
+    if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * G, st) != cudaSuccess) return HD_ERR_CUDA;
+    int ppi = 256 / (C / Vec<T>::N), chunks;
+    int64_t ppb = pick_chunk(N, HW, ppi, &chunks);
+    gn_stats_kernel<T><<<dim3(chunks, N), 256, 0, st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, N, HW, C, G, ppb, sums);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+extern "C" int hd_gn_stats(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, double* sums, cudaStream_t stream) {
+    HD_REQUIRE(in0 && sums && N > 0 && HW > 0 && C0 > 0 && (C1 == 0 || in1));
+    if (dtype == HD_F32) return gn_stats_t<float>(in0, C0, in1, C1, N, HW, G, sums, stream);
+    if (dtype == HD_BF16) return gn_stats_t<__nv_bfloat16>(in0, C0, in1, C1, N, HW, G, sums, stream);
+    return HD_ERR_ARG;
+}
+
+// ------------------------------- apply (forward) --------------------------------------------
+// out[n][pix][c] = drop( act( (x - mean) * rstd * gamma + beta ) ); grid (chunks, N)
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> x, GnParams g, T* out) {
+    constexpr int V = Vec<T>::N;
+    __shared__ float s_mean[64], s_rstd[64];
+    const int n = blockIdx.y;
+    gn_load_stats(g, n, s_mean, s_rstd);
+    __syncthreads();
+    const int lanes = g.C / V, cpg = g.C / g.G;
+    const int64_t nvec = g.HW * lanes;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = i / lanes; const int c0 = (int)(i - pix * lanes) * V;
+        float v[V]; vec_load(x.at(n, pix, g.HW, c0), v);
+        const int64_t obase = ((int64_t)n * g.HW + pix) * g.C + c0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            int c = c0 + k, gi = c / cpg;
+            float z = (v[k] - s_mean[gi]) * s_rstd[gi] * __ldg(g.gamma + c) + __ldg(g.beta + c);
+            if (g.act) z = hd_swish(z);
+            if (g.p_drop > 0.f) z *= hd_dropout_scale(g.seed, (uint64_t)(obase + k), g.p_drop);
+            v[k] = z;
+        }
+        vec_store(out + obase, v);
+    }
+}
+template <typename T>
+static int gn_apply_t(const void* in0, int C0, const void* in1, int C1, GnParams g, void* out, cudaStream_t st) {
+    int rc = gn_check<T>(C0, C1, g.G); if (rc) return rc;
+    int64_t nvec = g.HW * (g.C / Vec<T>::N);
+    int64_t chunks = (nvec + 1023) / 1024;
+    int64_t cap = ((int64_t)hd_num_sms() * 16 + g.N - 1) / g.N;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    gn_apply_kernel<T><<<dim3((unsigned)chunks, g.N), 256, 0, st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (T*)out);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+extern "C" int hd_gn_apply(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, const double* sums,
+                           const float* gamma, const float* beta, float eps, int act, float p_drop, uint64_t seed, void* out,
+                           cudaStream_t stream) {
+    HD_REQUIRE(in0 && sums && gamma && beta && out && N > 0 && HW > 0 && (C1 == 0 || in1));
+    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
+    if (dtype == HD_F32) return gn_apply_t<float>(in0, C0, in1, C1, g, out, stream);
+    if (dtype == HD_BF16) return gn_apply_t<__nv_bfloat16>(in0, C0, in1, C1, g, out, stream);
+    return HD_ERR_ARG;
+}
+
+// ------------------------------- backward, reduction pass -----------------------------------
+// dy' = dy * drop * act'(z).  Per channel: dgamma += sum dy' xhat, dbeta += sum dy'.
+// Per (n, group): gsums = (sum gamma dy', sum gamma dy' xhat).
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams g, const T* dy, int64_t pix_per_block,
+                                                            double* gsums, float* dgamma, float* dbeta) {
+    constexpr int V = Vec<T>::N;
+    __shared__ float s_mean[64], s_rstd[64], sg[64][2];
+    const int n = blockIdx.y;
+    gn_load_stats(g, n, s_mean, s_rstd);
+    for (int i = threadIdx.x; i < g.G; i += blockDim.x) { sg[i][0] = 0.f; sg[i][1] = 0.f; }
+    __syncthreads();
+    const int lanes = g.C / V, cpg = g.C / g.G;
+    const int ppi = blockDim.x / lanes;
+    const int lane = threadIdx.x % lanes, sub = threadIdx.x / lanes;
+    if (sub < ppi) {
+        const int c0 = lane * V;
+        float gam[V], bet[V], s1[V], s2[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) { gam[k] = g.gamma[c0 + k]; bet[k] = g.beta[c0 + k]; s1[k] = 0.f; s2[k] = 0.f; }
+        const int64_t p0 = blockIdx.x * pix_per_block;
+        const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
+        for (int64_t p = p0 + sub; p < p1; p += ppi) {
+            float v[V], d[V];
+            vec_load(x.at(n, p, g.HW, c0), v);
+            const int64_t obase = ((int64_t)n * g.HW + p) * g.C + c0;
+            vec_load(dy + obase, d);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                int gi = (c0 + k) / cpg;
+                float xh = (v[k] - s_mean[gi]) * s_rstd[gi];
+                float dd = d[k];
+                if (g.p_drop > 0.f) dd *= hd_dropout_scale(g.seed, (uint64_t)(obase + k), g.p_drop);
+                if (g.act) dd *= hd_swish_grad(xh * gam[k] + bet[k]);
+                s1[k] += dd; s2[k] += dd * xh;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            int c = c0 + k, gi = c / cpg;
+            atomicAdd(dgamma + c, s2[k]); atomicAdd(dbeta + c, s1[k]);
+            atomicAdd(&sg[gi][0], gam[k] * s1[k]); atomicAdd(&sg[gi][1], gam[k] * s2[k]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.G; i += blockDim.x) {
+        atomicAdd(gsums + ((int64_t)n * g.G + i) * 2, (double)sg[i][0]);
+        atomicAdd(gsums + ((int64_t)n * g.G + i) * 2 + 1, (double)sg[i][1]);
+    }
+}
+template <typename T>
+static int gn_bwd_reduce_t(const void* in0, int C0, const void* in1, int C1, GnParams g, const void* dy, double* gsums,
+                           float* dgamma, float* dbeta, cudaStream_t st) {
+    int rc = gn_check<T>(C0, C1, g.G); if (rc) return rc;
+    if (cudaMemsetAsync(gsums, 0, sizeof(double) * 2 * (size_t)g.N * g.G, st) != cudaSuccess) return HD_ERR_CUDA;
+    int ppi = 256 / (g.C / Vec<T>::N), chunks;
+    int64_t ppb = pick_chunk(g.N, g.HW, ppi, &chunks);
+    gn_bwd_reduce_kernel<T><<<dim3(chunks, g.N), 256, 0, st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (const T*)dy, ppb, gsums, dgamma, dbeta);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+extern "C" int hd_gn_bwd_reduce(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G,
+                                const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
+                                uint64_t seed, const void* dy, double* gsums, float* dgamma, float* dbeta, cudaStream_t stream) {
+    HD_REQUIRE(in0 && sums && gamma && beta && dy && gsums && dgamma && dbeta && (C1 == 0 || in1));
+    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
+    if (dtype == HD_F32) return gn_bwd_reduce_t<float>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, stream);
+    if (dtype == HD_BF16) return gn_bwd_reduce_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, stream);
+    return HD_ERR_ARG;
+}
+
+// ------------------------------- backward, apply pass ---------------------------------------
+// dx = rstd * (gamma dy' - A/m - xhat B/m) + add + acc ; written to two destination tensors.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g, const T* dy, const double* gsums, const T* add,
+                                                           const T* acc0, const T* acc1, T* dx0, T* dx1) {
+    constexpr int V = Vec<T>::N;
+    __shared__ float s_mean[64], s_rstd[64], s_a[64], s_b[64];
+    const int n = blockIdx.y;
+    gn_load_stats(g, n, s_mean, s_rstd);
+    const double m = (double)(g.C / g.G) * (double)g.HW;
+    for (int i = threadIdx.x; i < g.G; i += blockDim.x) {
+        s_a[i] = (float)(gsums[((int64_t)n * g.G + i) * 2] / m);
+        s_b[i] = (float)(gsums[((int64_t)n * g.G + i) * 2 + 1] / m);
+    }
+    __syncthreads();
+    const int lanes = g.C / V, cpg = g.C / g.G;
+    const int64_t nvec = g.HW * lanes;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = i / lanes; const int c0 = (int)(i - pix * lanes) * V;
+        float v[V], d[V], r[V];
+        vec_load(x.at(n, pix, g.HW, c0), v);
+        const int64_t obase = ((int64_t)n * g.HW + pix) * g.C + c0;
+        vec_load(dy + obase, d);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            int c = c0 + k, gi = c / cpg;
+            float gam = __ldg(g.gamma + c);
+            float xh = (v[k] - s_mean[gi]) * s_rstd[gi];
+            float dd = d[k];
+            if (g.p_drop > 0.f) dd *= hd_dropout_scale(g.seed, (uint64_t)(obase + k), g.p_drop);
+            if (g.act) dd *= hd_swish_grad(xh * gam + __ldg(g.beta + c));
+            r[k] = s_rstd[gi] * (gam * dd - s_a[gi] - xh * s_b[gi]);
+        }
+        if (add) { float a[V]; vec_load(add + obase, a);
+#pragma unroll
+            for (int k = 0; k < V; ++k) r[k] += a[k]; }
+        if (c0 < x.C0) {
+            const int64_t o = ((int64_t)n * g.HW + pix) * x.C0 + c0;
+            if (acc0) { float a[V]; vec_load(acc0 + o, a);
+#pragma unroll
+                for (int k = 0; k < V; ++k) r[k] += a[k]; }
+            vec_store(dx0 + o, r);
+        } else {
+            const int64_t o = ((int64_t)n * g.HW + pix) * x.C1 + (c0 - x.C0);
+            if (acc1) { float a[V]; vec_load(acc1 + o, a);
+#pragma unroll
+                for (int k = 0; k < V; ++k) r[k] += a[k]; }
+            vec_store(dx1 + o, r);
+        }
+    }
+}
+template <typename T>
+static int gn_bwd_apply_t(const void* in0, int C0, const void* in1, int C1, GnParams g, const void* dy, const double* gsums,
+                          const void* add, const void* acc0, const void* acc1, void* dx0, void* dx1, cudaStream_t st) {
+    int rc = gn_check<T>(C0, C1, g.G); if (rc) return rc;
+    int64_t nvec = g.HW * (g.C / Vec<T>::N);
+    int64_t chunks = (nvec + 1023) / 1024;
+    int64_t cap = ((int64_t)hd_num_sms() * 16 + g.N - 1) / g.N;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    gn_bwd_apply_kernel<T><<<dim3((unsigned)chunks, g.N), 256, 0, st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (const T*)dy, gsums,
+                                                                  (const T*)add, (const T*)acc0, (const T*)acc1, (T*)dx0, (T*)dx1);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+extern "C" int hd_gn_bwd_apply(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G,
+                               const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
+                               uint64_t seed, const void* dy, const double* gsums, const void* add, const void* acc0,
+                               const void* acc1, void* dx0, void* dx1, cudaStream_t stream) {
+    HD_REQUIRE(in0 && sums && gamma && beta && dy && gsums && dx0 && (C1 == 0 || (in1 && dx1)));
+    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
+    if (dtype == HD_F32) return gn_bwd_apply_t<float>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, stream);
+    if (dtype == HD_BF16) return gn_bwd_apply_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, stream);
+    return HD_ERR_ARG;
+}
+
+// ------------------------------- column sums -------------------------------------------------
+// per_n[n][c] = sum_pix t[n][pix][c] (optional);  total[c] += sum_n per_n[n][c] (optional)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* t, int N, int64_t HW, int C, int64_t pix_per_block, float* per_n, int64_t ld, float* total) {
+    constexpr int V = Vec<T>::N;
+    const int lanes = C / V, ppi = blockDim.x / lanes;
+    const int lane = threadIdx.x % lanes, sub = threadIdx.x / lanes, n = blockIdx.y;
+    if (sub >= ppi) return;
+    float s[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) s[k] = 0.f;
+    const int64_t p0 = blockIdx.x * pix_per_block;
+    const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
+    for (int64_t p = p0 + sub; p < p1; p += ppi) {
+        float v[V]; vec_load(t + ((int64_t)n * HW + p) * C + lane * V, v);
+#pragma unroll
+        for (int k = 0; k < V; ++k) s[k] += v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        if (per_n) atomicAdd(per_n + (int64_t)n * ld + lane * V + k, s[k]);
+        if (total) atomicAdd(total + lane * V + k, s[k]);
+    }
+}
+__global__ void colsum_nchw_kernel(const float* t, int C, int64_t HW, float* per_n, int64_t ld, float* total) {
+    // block per (n, c)
+    __shared__ float red[8];
+    const int c = blockIdx.x, n = blockIdx.y;
+    const float* p = t + ((int64_t)n * C + c) * HW;
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) s += p[i];
+    s = hd_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
+        if (per_n) atomicAdd(per_n + (int64_t)n * ld + c, tot);
+        if (total) atomicAdd(total + c, tot);
+    }
+}
+// Both outputs ACCUMULATE (atomics): the caller zeroes them (they live in the flat gradient buffers).
+extern "C" int hd_colsum(int dtype, const void* t, int nchw_f32, int N, int64_t HW, int C, float* per_n, int64_t ld_per_n, float* total, cudaStream_t stream) {
+    HD_REQUIRE(t && (per_n || total) && N > 0 && HW > 0 && C > 0);
+    if (nchw_f32) {
+        colsum_nchw_kernel<<<dim3(C, N), 256, 0, stream>>>((const float*)t, C, HW, per_n, ld_per_n, total);
+        HD_CHECK_LAUNCH();
+        return HD_OK;
+    }
+    int V = dtype == HD_F32 ? 4 : 8;
+    if (C % V != 0 || C / V > 256) { hd_set_error("colsum: unsupported channel count"); return HD_ERR_UNSUPPORTED; }
+    int ppi = 256 / (C / V), chunks;
+    int64_t ppb = pick_chunk(N, HW, ppi, &chunks);
+    if (dtype == HD_F32) colsum_kernel<float><<<dim3(chunks, N), 256, 0, stream>>>((const float*)t, N, HW, C, ppb, per_n, ld_per_n, total);
+    else if (dtype == HD_BF16) colsum_kernel<__nv_bfloat16><<<dim3(chunks, N), 256, 0, stream>>>((const __nv_bfloat16*)t, N, HW, C, ppb, per_n, ld_per_n, total);
+    else return HD_ERR_ARG;
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+
+// ------------------------------- K6: q_sample / MSE ------------------------------------------
+// x_t = sqrt_ab[t[n]] * x0 + sqrt_1m_ab[t[n]] * noise     (fp32 NCHW, chw elements per sample)
+__global__ void q_sample_kernel(const float4* x0, const float4* noise, const int64_t* t, const float* sab, const float* s1ab,
+                                float4* xt, int64_t chw4) {
+    const int n = blockIdx.y;
+    const float a = sab[t[n]], b = s1ab[t[n]];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < chw4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 u = x0[n * chw4 + i], v = noise[n * chw4 + i];
+        xt[n * chw4 + i] = make_float4(a * u.x + b * v.x, a * u.y + b * v.y, a * u.z + b * v.z, a * u.w + b * v.w);
+    }
+}
+extern "C" int hd_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sab, const float* s1ab, float* xt,
+                           int N, int64_t chw, cudaStream_t stream) {
+    HD_REQUIRE(x0 && noise && t && sab && s1ab && xt && N > 0 && chw > 0 && chw % 4 == 0);
+    int64_t chw4 = chw / 4;
+    int64_t bx = (chw4 + 255) / 256; if (bx > 1024) bx = 1024;
+    q_sample_kernel<<<dim3((unsigned)bx, N), 256, 0, stream>>>((const float4*)x0, (const float4*)noise, t, sab, s1ab, (float4*)xt, chw4);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+// loss = (pred - noise)^2 ; dpred = 2 (pred - noise) * g
+__global__ void mse_fwd_kernel(const float4* pred, const float4* noise, float4* loss, int64_t n4) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 p = pred[i], q = noise[i];
+        float4 d = make_float4(p.x - q.x, p.y - q.y, p.z - q.z, p.w - q.w);
+        loss[i] = make_float4(d.x * d.x, d.y * d.y, d.z * d.z, d.w * d.w);
+    }
+}
+__global__ void mse_bwd_kernel(const float4* pred, const float4* noise, const float4* g, float4* dpred, int64_t n4) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 p = pred[i], q = noise[i], w = g[i];
+        dpred[i] = make_float4(2.f * (p.x - q.x) * w.x, 2.f * (p.y - q.y) * w.y, 2.f * (p.z - q.z) * w.z, 2.f * (p.w - q.w) * w.w);
+    }
+}
+extern "C" int hd_mse_fwd(const float* pred, const float* noise, float* loss, int64_t n, cudaStream_t stream) {
+    HD_REQUIRE(pred && noise && loss && n > 0 && n % 4 == 0);
+    int64_t b = (n / 4 + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+    mse_fwd_kernel<<<(unsigned)b, 256, 0, stream>>>((const float4*)pred, (const float4*)noise, (float4*)loss, n / 4);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+extern "C" int hd_mse_bwd(const float* pred, const float* noise, const float* g, float* dpred, int64_t n, cudaStream_t stream) {
+    HD_REQUIRE(pred && noise && g && dpred && n > 0 && n % 4 == 0);
+    int64_t b = (n / 4 + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+    mse_bwd_kernel<<<(unsigned)b, 256, 0, stream>>>((const float4*)pred, (const float4*)noise, (const float4*)g, (float4*)dpred, n / 4);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+
+// ------------------------------- K7: sampler step --------------------------------------------
+// eps = w1 eps_c - w eps_u (w1 = fp32(1+w), rounded on the host like torch does) ; mean = c1 x - c2 eps ; x' = mean + sqrt_var z ; NaN flag ; final clip.
+// coef points at a device table [T][3] = (coeff1, coeff2, sqrt(var)); the step index is read
+// from device memory so that one captured CUDA graph serves every time step.
+__global__ void sampler_step_kernel(float4* x, const float4* eps_c, const float4* eps_u, const float4* z, float w1, float w,
+                                    const float* coef, const int* step_ptr, int last_step_clip, int* nan_flag, int64_t n4) {
+    const int step = *step_ptr;
+    const float c1 = coef[step * 3], c2 = coef[step * 3 + 1], sv = coef[step * 3 + 2];
+    const bool last = (step == 0);
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 xv = x[i], e = eps_c[i];
+        if (eps_u) { float4 u = eps_u[i]; e = make_float4(w1 * e.x - w * u.x, w1 * e.y - w * u.y, w1 * e.z - w * u.z, w1 * e.w - w * u.w); }
+        float4 r = make_float4(c1 * xv.x - c2 * e.x, c1 * xv.y - c2 * e.y, c1 * xv.z - c2 * e.z, c1 * xv.w - c2 * e.w);
+        if (!last) { float4 zz = z[i]; r.x += sv * zz.x; r.y += sv * zz.y; r.z += sv * zz.z; r.w += sv * zz.w; }
+        bad |= isnan(r.x) | isnan(r.y) | isnan(r.z) | isnan(r.w);
+        if (last && last_step_clip) {
+            r.x = fminf(fmaxf(r.x, -1.f), 1.f); r.y = fminf(fmaxf(r.y, -1.f), 1.f);
+            r.z = fminf(fmaxf(r.z, -1.f), 1.f); r.w = fminf(fmaxf(r.w, -1.f), 1.f);
+        }
+        x[i] = r;
+    }
+    if (bad) atomicOr(nan_flag, 1);
+}
+extern "C" int hd_sampler_step(float* x, const float* eps_c, const float* eps_u, const float* z, float w1, float w, const float* coef,
+                               const int* step_ptr, int last_step_clip, int* nan_flag, int64_t n, cudaStream_t stream) {
+    HD_REQUIRE(x && eps_c && z && coef && step_ptr && nan_flag && n > 0 && n % 4 == 0);
+    int64_t b = (n / 4 + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+    sampler_step_kernel<<<(unsigned)b, 256, 0, stream>>>((float4*)x, (const float4*)eps_c, (const float4*)eps_u, (const float4*)z, w1, w, coef,
+                                                         step_ptr, last_step_clip, nan_flag, n / 4);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+__global__ void add_int_kernel(int* p, int delta) { *p += delta; }
+extern "C" int hd_add_int(int* p, int delta, cudaStream_t stream) {
+    HD_REQUIRE(p);
+    add_int_kernel<<<1, 1, 0, stream>>>(p, delta);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+
+// ------------------------------- fused clip + AdamW on flat buffers --------------------------
+__global__ void sqnorm_kernel(const float4* g, int64_t n4, double* out) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = g[i]; s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    s = hd_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w]; atomicAdd(out, (double)t); }
+}
+extern "C" int hd_sqnorm(const float* g, int64_t n, double* out, cudaStream_t stream) {
+    HD_REQUIRE(g && out && n > 0 && n % 4 == 0);
+    if (cudaMemsetAsync(out, 0, sizeof(double), stream) != cudaSuccess) return HD_ERR_CUDA;
+    int64_t b = (n / 4 + 255) / 256; if (b > 148 * 8) b = 148 * 8;
+    sqnorm_kernel<<<(unsigned)b, 256, 0, stream>>>((const float4*)g, n / 4, out);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+// torch.nn.utils.clip_grad_norm_(max_norm) followed by torch.optim.AdamW (decoupled weight decay):
+//   clip = min(1, max_norm / (||g|| + 1e-6)); g *= clip
+//   p *= 1 - lr wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void adamw_kernel(float4* p, float4* g, float4* m, float4* v, int64_t n4, const double* sqnorm, float max_norm,
+                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+    float clip = 1.f;
+    if (max_norm > 0.f) { float nrm = (float)sqrt(*sqnorm); clip = fminf(1.f, max_norm / (nrm + 1e-6f)); }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
+        float* pp = &pv.x; float* gg = &gv.x; float* mm = &mv.x; float* vq = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float gk = gg[k] * clip;
+            gg[k] = gk;
+            pp[k] *= 1.f - lr * wd;
+            mm[k] = b1 * mm[k] + (1.f - b1) * gk;
+            vq[k] = b2 * vq[k] + (1.f - b2) * gk * gk;
+            float denom = sqrtf(vq[k]) / bc2_sqrt + eps;
+            pp[k] -= (lr / bc1) * (mm[k] / denom);
+        }
+        p[i] = pv; g[i] = gv; m[i] = mv; v[i] = vv;
+    }
+}
+extern "C" int hd_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const double* sqnorm, float max_norm, float lr,
+                             float b1, float b2, float eps, float wd, int step, cudaStream_t stream) {
+    HD_REQUIRE(p && g && m && v && n > 0 && n % 4 == 0 && step >= 1 && (max_norm <= 0.f || sqnorm));
+    float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+    int64_t b = (n / 4 + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+    adamw_kernel<<<(unsigned)b, 256, 0, stream>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n / 4, sqnorm, max_norm, lr, b1, b2, eps, wd, bc1, sqrtf(bc2));
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}

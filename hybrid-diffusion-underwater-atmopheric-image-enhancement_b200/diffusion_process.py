@@ -1,0 +1,152 @@
+"""DDPM forward-noising trainer (Algorithm 1) and classifier-free-guidance ancestral sampler
+(Algorithm 2) on the hdiff_b200 kernels.
+
+Reference followed (paths relative to the reference repository):
+  extract                      DiffusionFreeGuidence/DiffusionCondition.py:9-16   (dup diffusion/Diffusion.py:16-23)
+  GaussianDiffusionTrainer     DiffusionFreeGuidence/DiffusionCondition.py:19-46  (uncond twin diffusion/Diffusion.py:304-314)
+  GaussianDiffusionSampler     DiffusionFreeGuidence/DiffusionCondition.py:49-98  (uncond twin diffusion/Diffusion.py:351-368)
+
+Differences kept deliberately: the per-step `print` (:88) is dropped and the per-step NaN
+assertion (:96, a device->host sync) becomes a device flag checked once after the last step.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops as _ops
+
+
+def extract(v, t, x_shape):
+    """gather(v, t) -> fp32 -> [B,1,1,...]  (DiffusionCondition.py:9-16)."""
+    out = torch.gather(v, index=t, dim=0).float().to(t.device)
+    return out.view([t.shape[0]] + [1] * (len(x_shape) - 1))
+
+
+def schedule_tables(beta_1, beta_T, T):
+    """float64 tables; linspace is evaluated in fp32 and only then cast (DiffusionCondition.py:26-35,58-66)."""
+    betas = torch.linspace(beta_1, beta_T, T).double()
+    alphas = 1. - betas
+    alphas_bar = torch.cumprod(alphas, dim=0)
+    alphas_bar_prev = F.pad(alphas_bar, [1, 0], value=1)[:T]
+    coeff1 = torch.sqrt(1. / alphas)
+    return {
+        "betas": betas,
+        "sqrt_alphas_bar": torch.sqrt(alphas_bar),
+        "sqrt_one_minus_alphas_bar": torch.sqrt(1. - alphas_bar),
+        "coeff1": coeff1,
+        "coeff2": coeff1 * (1. - alphas) / torch.sqrt(1. - alphas_bar),
+        "posterior_var": betas * (1. - alphas_bar_prev) / (1. - alphas_bar),
+    }
+
+
+class _MseFn(torch.autograd.Function):
+    """F.mse_loss(pred, noise, reduction='none') with its gradient, one kernel each (K6)."""
+
+    @staticmethod
+    def forward(ctx, pred, noise):
+        pred = pred.contiguous()
+        loss = torch.empty_like(pred)
+        _ops.get().mse_fwd(pred, noise, loss)
+        ctx.save_for_backward(pred, noise)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, noise = ctx.saved_tensors
+        g = g.expand_as(pred).contiguous()
+        d = torch.empty_like(pred)
+        _ops.get().mse_bwd(pred, noise, g, d)
+        return d, None
+
+
+class GaussianDiffusionTrainer(nn.Module):
+    """GaussianDiffusionTrainer(model, beta_1, beta_T, T).forward(x_0[, labels]) -> unreduced loss [B,3,H,W].
+    RNG order as in the reference: randint, then randn_like, both on x_0's device generator."""
+
+    def __init__(self, model, beta_1, beta_T, T):
+        super().__init__()
+        self.model = model
+        self.T = T
+        tab = schedule_tables(beta_1, beta_T, T)
+        self.register_buffer('betas', tab["betas"])
+        self.register_buffer('sqrt_alphas_bar', tab["sqrt_alphas_bar"])
+        self.register_buffer('sqrt_one_minus_alphas_bar', tab["sqrt_one_minus_alphas_bar"])
+        # what extract() hands to the arithmetic: the f64 entries rounded to fp32
+        self.register_buffer('_sab32', tab["sqrt_alphas_bar"].float(), persistent=False)
+        self.register_buffer('_s1ab32', tab["sqrt_one_minus_alphas_bar"].float(), persistent=False)
+
+    def forward(self, x_0, labels=None):
+        assert x_0.dtype == torch.float32
+        x_0 = x_0.contiguous()
+        t = torch.randint(self.T, size=(x_0.shape[0], ), device=x_0.device)
+        noise = torch.randn_like(x_0)
+        x_t = torch.empty_like(x_0)
+        _ops.get().q_sample(x_0, noise, t, self._sab32, self._s1ab32, x_t)
+        pred = self.model(x_t, t) if labels is None else self.model(x_t, t, labels)
+        return _MseFn.apply(pred, noise)
+
+
+class GaussianDiffusionSampler(nn.Module):
+    """GaussianDiffusionSampler(model, beta_1, beta_T, T[, w]).forward(x_T[, labels]) -> x_0 in [-1, 1].
+    With labels, each step evaluates the conditional and the null-label (0) network as ONE batch of 2B."""
+
+    def __init__(self, model, beta_1, beta_T, T, w=0.):
+        super().__init__()
+        self.model = model
+        self.T = T
+        self.w = w
+        tab = schedule_tables(beta_1, beta_T, T)
+        self.register_buffer('betas', tab["betas"])
+        self.register_buffer('coeff1', tab["coeff1"])
+        self.register_buffer('coeff2', tab["coeff2"])
+        self.register_buffer('posterior_var', tab["posterior_var"])
+        var = torch.cat([tab["posterior_var"][1:2], tab["betas"][1:]])          # DiffusionCondition.py:74
+        coef = torch.stack([tab["coeff1"].float(), tab["coeff2"].float(), torch.sqrt(var.float())], dim=1).contiguous()
+        self.register_buffer('_coef', coef, persistent=False)                    # [T][3] fp32
+
+    def predict_xt_prev_mean_from_eps(self, x_t, t, eps):
+        assert x_t.shape == eps.shape
+        return extract(self.coeff1, t, x_t.shape) * x_t - extract(self.coeff2, t, x_t.shape) * eps
+
+    def _eps_pair(self, x, t, labels):
+        """(eps_cond, eps_uncond) — batched as 2B when the model accepts it."""
+        B = x.shape[0]
+        if getattr(self.model, "cfg_batched", True):
+            e = self.model(torch.cat([x, x], 0), torch.cat([t, t], 0), torch.cat([labels, torch.zeros_like(labels)], 0))
+            return e[:B], e[B:]
+        return self.model(x, t, labels), self.model(x, t, torch.zeros_like(labels))
+
+    def forward(self, x_T, labels=None):
+        ops = _ops.get()
+        assert x_T.dtype == torch.float32
+        dev = x_T.device
+        x = x_T.clone().contiguous()
+        B = x.shape[0]
+        step = torch.full((1,), self.T - 1, dtype=torch.int32, device=dev)
+        nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        frozen = self.model.frozen_weights() if hasattr(self.model, "frozen_weights") else _Null()
+        with torch.no_grad(), frozen:
+            for time_step in reversed(range(self.T)):
+                t = x.new_full([B, ], time_step, dtype=torch.long)
+                if labels is None:
+                    eps_c, eps_u = self.model(x, t), None
+                else:
+                    eps_c, eps_u = self._eps_pair(x, t, labels)
+                    eps_u = eps_u.contiguous()
+                eps_c = eps_c.contiguous()
+                assert eps_c.shape == x.shape
+                z = torch.randn_like(x) if time_step > 0 else x
+                ops.sampler_step(x, eps_c, eps_u, z, self.w, self._coef, step, True, nan_flag)
+                ops.add_int(step, -1)
+        assert int(nan_flag.item()) == 0, "nan in tensor."
+        return x
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

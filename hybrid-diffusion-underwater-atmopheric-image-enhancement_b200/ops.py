@@ -1,0 +1,221 @@
+"""Operator layer of the hot path: one Python method per C-ABI entry point.
+
+All activations are NHWC tensors of the compute dtype (bf16, or fp32 in check mode); the
+3-channel network input / output stay NCHW fp32 as in the reference API.  A *view* argument
+`P` (1 or 2) exposes a tensor through its 2x2 space-to-depth rearrangement, which
+turns the reference's strided and transposed convolutions into stride-1 convolutions.
+
+`CudaOps` is the only backend of the product.  It raises if the CUDA library is missing.  Tests
+install a torch re-statement of these methods (tests/emu_backend.py) to exercise the host logic on
+machines without a GPU; nothing in this package refers to it.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class CudaOps:
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.use_tc = True          # tcgen05 kernels where the shape is covered
+        self.launches = 0           # kernels launched through this object (bench.py reports it)
+        self.tc_launches = 0
+
+    # ---- convolution family -------------------------------------------------------------
+    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False):
+        """out = conv_k(view(x0|x1, P_in)) + bias + emb[:, :, None, None] + res, logical stride 1, 'same' padding.
+        w: packed [CoutL][k*k][CinL] in the compute dtype.  H, W are the LOGICAL spatial dims."""
+        dt = _DT[w.dtype]
+        C0 = x0.shape[1] if in_nchw else x0.shape[-1]
+        C1 = 0 if x1 is None else x1.shape[-1]
+        Cout = out.shape[1] if out_nchw else out.shape[-1]
+        lib = self.lib
+        if (self.use_tc and dt == BF16 and not in_nchw and not out_nchw
+                and lib.hd_conv_tc_supported(C0, C1, P_in, Cout, P_out, H, W, k)):
+            rc = lib.hd_conv_tc(_p(x0), C0, _p(x1), C1, P_in, _p(w), _p(bias), _p(emb),
+                                0 if emb is None else emb.stride(0), _p(res), _p(out), Cout, P_out,
+                                N, H, W, k, _stream())
+            _lib.check(rc, "hd_conv_tc")
+            self.launches += 1
+            self.tc_launches += 1
+            return
+        rc = lib.hd_conv_simt(dt, _p(x0), C0, _p(x1), C1, P_in, int(in_nchw), _p(w), _p(bias), _p(emb),
+                              0 if emb is None else emb.stride(0), _p(res), _p(out), Cout, P_out, int(out_nchw),
+                              N, H, W, k, _stream())
+        _lib.check(rc, "hd_conv_simt")
+        self.launches += 1
+
+    def wgrad(self, x0, x1, P_in, dy, P_dy, dw, N, H, W, k, dtype, in_nchw=False, dy_nchw=False, workspace=None):
+        """dw[CoutL][k*k][CinL] (fp32, overwritten) = sum over pixels of dy (x) shifted input."""
+        dt = _DT[dtype]
+        C0 = x0.shape[1] if in_nchw else x0.shape[-1]
+        C1 = 0 if x1 is None else x1.shape[-1]
+        Cdy = dy.shape[1] if dy_nchw else dy.shape[-1]
+        lib = self.lib
+        if (self.use_tc and dt == BF16 and not in_nchw and not dy_nchw
+                and lib.hd_wgrad_tc_supported(C0, C1, P_in, Cdy, P_dy, H, W, k)):
+            need = lib.hd_wgrad_tc_workspace(C0, C1, P_in, Cdy, P_dy, N * H * W, W, k)
+            if workspace is None or workspace.numel() * 4 < need:
+                workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=dw.device)
+            rc = lib.hd_wgrad_tc(_p(x0), C0, _p(x1), C1, P_in, _p(dy), Cdy, P_dy, _p(dw), _p(workspace),
+                                 workspace.numel() * 4, N, H, W, k, _stream())
+            _lib.check(rc, "hd_wgrad_tc")
+            self.launches += 2
+            self.tc_launches += 1
+            return
+        rc = lib.hd_wgrad_simt(dt, _p(x0), C0, _p(x1), C1, P_in, int(in_nchw), _p(dy), Cdy, P_dy, int(dy_nchw),
+                               _p(dw), N, H, W, k, _stream())
+        _lib.check(rc, "hd_wgrad_simt")
+        self.launches += 1
+
+    # ---- attention -----------------------------------------------------------------------
+    def attn_fwd(self, qkv, out, lse, N, S, C):
+        if self.use_tc and qkv.dtype == torch.bfloat16 and self.lib.hd_attn_tc_supported(S, C):
+            _lib.check(self.lib.hd_attn_fwd_tc(_p(qkv), _p(out), _p(lse), N, S, C, _stream()), "hd_attn_fwd_tc")
+            self.tc_launches += 1
+        else:
+            _lib.check(self.lib.hd_attn_fwd_simt(_DT[qkv.dtype], _p(qkv), _p(out), _p(lse), N, S, C, _stream()), "hd_attn_fwd_simt")
+        self.launches += 1
+
+    def attn_bwd(self, qkv, out, dout, lse, delta, dqkv, N, S, C):
+        if self.use_tc and qkv.dtype == torch.bfloat16 and self.lib.hd_attn_tc_supported(S, C):
+            _lib.check(self.lib.hd_attn_bwd_tc(_p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), N, S, C, _stream()), "hd_attn_bwd_tc")
+            self.tc_launches += 2
+        else:
+            _lib.check(self.lib.hd_attn_bwd_simt(_DT[qkv.dtype], _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), N, S, C, _stream()), "hd_attn_bwd_simt")
+        self.launches += 3
+
+    # ---- GroupNorm family ----------------------------------------------------------------
+    def gn_stats(self, x0, x1, N, HW, G, sums):
+        C0, C1 = x0.shape[-1], 0 if x1 is None else x1.shape[-1]
+        _lib.check(self.lib.hd_gn_stats(_DT[x0.dtype], _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _stream()), "hd_gn_stats")
+        self.launches += 1
+
+    def gn_apply(self, x0, x1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, out):
+        C0, C1 = x0.shape[-1], 0 if x1 is None else x1.shape[-1]
+        _lib.check(self.lib.hd_gn_apply(_DT[x0.dtype], _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _p(gamma), _p(beta),
+                                        eps, int(act), float(p_drop), int(seed), _p(out), _stream()), "hd_gn_apply")
+        self.launches += 1
+
+    def gn_bwd(self, x0, x1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, dy, gsums, dgamma, dbeta,
+               add, acc0, acc1, dx0, dx1):
+        """dgamma/dbeta accumulate; dx0/dx1 are overwritten with dx (+ add + acc0/acc1)."""
+        C0, C1 = x0.shape[-1], 0 if x1 is None else x1.shape[-1]
+        dt = _DT[x0.dtype]
+        _lib.check(self.lib.hd_gn_bwd_reduce(dt, _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _p(gamma), _p(beta), eps,
+                                             int(act), float(p_drop), int(seed), _p(dy), _p(gsums), _p(dgamma), _p(dbeta),
+                                             _stream()), "hd_gn_bwd_reduce")
+        _lib.check(self.lib.hd_gn_bwd_apply(dt, _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _p(gamma), _p(beta), eps,
+                                            int(act), float(p_drop), int(seed), _p(dy), _p(gsums), _p(add), _p(acc0), _p(acc1),
+                                            _p(dx0), _p(dx1), _stream()), "hd_gn_bwd_apply")
+        self.launches += 2
+
+    def colsum(self, t, N, HW, C, per_n, total, nchw=False):
+        """per_n[n, c] += sum_pix t ; total[c] += sum_{n,pix} t   (either may be None)."""
+        _lib.check(self.lib.hd_colsum(_DT[t.dtype], _p(t), int(nchw), N, HW, C, _p(per_n),
+                                      0 if per_n is None else per_n.stride(0), _p(total), _stream()), "hd_colsum")
+        self.launches += 1
+
+    # ---- embedding path (fp32) -----------------------------------------------------------
+    def linear_fwd(self, x, w, b, y, in_swish=False, accumulate=False):
+        M, K = x.shape
+        _lib.check(self.lib.hd_linear_fwd(_p(x), M, K, x.stride(0), _p(w), _p(b), _p(y), w.shape[0], y.stride(0),
+                                          int(in_swish), int(accumulate), _stream()), "hd_linear_fwd")
+        self.launches += 1
+
+    def linear_bwd_x(self, dy, w, x_pre, dx, accumulate=False):
+        M, Nout = dy.shape
+        K = w.shape[1]
+        _lib.check(self.lib.hd_linear_bwd_x(_p(dy), M, Nout, dy.stride(0), _p(w), K, _p(x_pre),
+                                            0 if x_pre is None else x_pre.stride(0), _p(dx), dx.stride(0),
+                                            int(accumulate), _stream()), "hd_linear_bwd_x")
+        self.launches += 1
+
+    def linear_bwd_w(self, dy, x, dw, db, in_swish=False):
+        M, Nout = dy.shape
+        K = x.shape[1]
+        _lib.check(self.lib.hd_linear_bwd_w(_p(dy), M, Nout, dy.stride(0), _p(x), K, x.stride(0), int(in_swish),
+                                            _p(dw), _p(db), _stream()), "hd_linear_bwd_w")
+        self.launches += 1
+
+    def embedding_fwd(self, table, idx, out):
+        _lib.check(self.lib.hd_embedding_fwd(_p(table), table.shape[0], table.shape[1], _p(idx), idx.numel(), _p(out), _stream()), "hd_embedding_fwd")
+        self.launches += 1
+
+    def embedding_bwd(self, dout, idx, dtable, padding_idx=-1):
+        _lib.check(self.lib.hd_embedding_bwd(_p(dout), dout.shape[1], _p(idx), idx.numel(), _p(dtable), padding_idx, _stream()), "hd_embedding_bwd")
+        self.launches += 1
+
+    # ---- parameter packing ---------------------------------------------------------------
+    def gather_pack(self, src, ia, ib, out):
+        _lib.check(self.lib.hd_gather_pack(_DT[out.dtype], _p(src), _p(ia), _p(ib), out.numel(), _p(out), _stream()), "hd_gather_pack")
+        self.launches += 1
+
+    def scatter_unpack(self, packed, inv, dst):
+        _lib.check(self.lib.hd_scatter_unpack(_p(packed), _p(inv), dst.numel(), _p(dst), _stream()), "hd_scatter_unpack")
+        self.launches += 1
+
+    # ---- diffusion process ---------------------------------------------------------------
+    def q_sample(self, x0, noise, t, sab, s1ab, xt):
+        N = x0.shape[0]
+        _lib.check(self.lib.hd_q_sample(_p(x0), _p(noise), _p(t), _p(sab), _p(s1ab), _p(xt), N, x0.numel() // N, _stream()), "hd_q_sample")
+        self.launches += 1
+
+    def mse_fwd(self, pred, noise, loss):
+        _lib.check(self.lib.hd_mse_fwd(_p(pred), _p(noise), _p(loss), pred.numel(), _stream()), "hd_mse_fwd")
+        self.launches += 1
+
+    def mse_bwd(self, pred, noise, g, dpred):
+        _lib.check(self.lib.hd_mse_bwd(_p(pred), _p(noise), _p(g), _p(dpred), pred.numel(), _stream()), "hd_mse_bwd")
+        self.launches += 1
+
+    def sampler_step(self, x, eps_c, eps_u, z, w, coef, step_ptr, clip_last, nan_flag):
+        _lib.check(self.lib.hd_sampler_step(_p(x), _p(eps_c), _p(eps_u), _p(z), float(1.0 + w), float(w), _p(coef), _p(step_ptr),
+                                            int(clip_last), _p(nan_flag), x.numel(), _stream()), "hd_sampler_step")
+        self.launches += 1
+
+    def add_int(self, p, delta):
+        _lib.check(self.lib.hd_add_int(_p(p), int(delta), _stream()), "hd_add_int")
+        self.launches += 1
+
+    # ---- optimizer -----------------------------------------------------------------------
+    def sqnorm(self, g, out):
+        _lib.check(self.lib.hd_sqnorm(_p(g), g.numel(), _p(out), _stream()), "hd_sqnorm")
+        self.launches += 1
+
+    def adamw_flat(self, p, g, m, v, sqnorm, max_norm, lr, b1, b2, eps, wd, step):
+        _lib.check(self.lib.hd_adamw_flat(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(sqnorm), float(max_norm), float(lr),
+                                          float(b1), float(b2), float(eps), float(wd), int(step), _stream()), "hd_adamw_flat")
+        self.launches += 1
+
+
+_backend = None
+
+
+def get():
+    """The operator backend.  Created on first use; fails loudly when the CUDA library is absent."""
+    global _backend
+    if _backend is None:
+        _backend = CudaOps()
+    return _backend
+
+
+def set_backend(b):
+    """Test hook (tests/emu_backend.py installs a torch re-statement for CPU-only host-logic tests)."""
+    global _backend
+    _backend = b

@@ -1,0 +1,147 @@
+"""CPU tests of the host logic (kernel schedule, packed layouts, views, flat buffers) with the torch test
+double of the operator layer (tests/emu_backend.py) standing in for the CUDA library.  The reference
+numbers come from the golden fixtures minted from the reference itself and from the oracle."""
+import os
+
+import pytest
+import torch
+
+import hdiff_b200.ops as hops
+from hdiff_b200.diffusion.Model import UNet as UNetU
+from hdiff_b200.DiffusionFreeGuidence.ModelCondition import UNet as UNetC
+from hdiff_b200.DiffusionFreeGuidence.DiffusionCondition import GaussianDiffusionTrainer, GaussianDiffusionSampler
+from oracle import ref_torch as R
+from tests.emu_backend import EmuOps
+
+
+@pytest.fixture(autouse=True)
+def emu():
+    prev = hops._backend
+    hops.set_backend(EmuOps())
+    yield
+    hops.set_backend(prev)
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _close(a, b, rtol, atol=2e-5):
+    """relative error in the 2-norm, with an absolute floor: several reference gradients are
+    mathematically zero (a bias feeding a per-channel GroupNorm, proj_k.bias under softmax)."""
+    d = float((a - b).norm())
+    return d <= rtol * float(b.norm()) + atol
+
+
+def test_state_dict_keys_match_oracle():
+    for cfg in (dict(T=100, ch=32, ch_mult=[1, 1], attn=[1], num_res_blocks=1, dropout=0.0),
+                dict(T=1000, ch=64, ch_mult=[1, 2, 2, 2], attn=[1], num_res_blocks=2, dropout=0.1)):
+        a = UNetC(num_labels=10, compute_dtype=torch.float32, **cfg)
+        b = R.UNet(num_labels=10, **cfg)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys())
+        assert all(sa[k].shape == sb[k].shape for k in sa)
+        u = UNetU(compute_dtype=torch.float32, **cfg)
+        assert list(u.state_dict().keys()) == list(R.UNet(**cfg).state_dict().keys())
+
+
+@pytest.mark.parametrize("tag", ["cond", "uncond"])
+def test_unet_tiny_forward_backward_vs_reference_golden(golden_dir, tag):
+    g = _load(golden_dir, "unet_tiny.pt")
+    cfg = g["cfg"]
+    if tag == "cond":
+        net = UNetC(num_labels=10, compute_dtype=torch.float32, **cfg)
+        net.load_state_dict(g["sd"])
+    else:
+        net = UNetU(compute_dtype=torch.float32, **cfg)
+        net.load_state_dict({k: v for k, v in g["sd"].items() if not k.startswith("cond_embedding.")})
+    net.train()
+    rec = g[tag]
+    eps = net(g["x"], g["t"]) if rec["labels"] is None else net(g["x"], g["t"], rec["labels"])
+    assert _rel(eps.detach(), rec["eps"]) < 2e-5
+    (eps ** 2).sum().backward()
+    params = dict(net.named_parameters())
+    for k, gref in rec["grads"].items():
+        assert params[k].grad is not None, k
+        assert _close(params[k].grad, gref, 1e-4), (k, _rel(params[k].grad, gref))
+    for k, sq in rec["grad_sqnorm"].items():
+        mine = float((params[k].grad.double() ** 2).sum())
+        assert abs(mine - sq) <= 4e-4 * sq + 1e-9, (k, mine, sq)
+    # parameters the reference leaves without gradient stay without gradient
+    for k, p in params.items():
+        if k not in rec["grad_sqnorm"]:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+
+
+def test_trainer_and_sampler_vs_reference_golden(golden_dir):
+    g = _load(golden_dir, "unet_tiny.pt")
+    net = UNetC(num_labels=10, compute_dtype=torch.float32, **g["cfg"])
+    net.load_state_dict(g["sd"])
+    net.train()
+    torch.manual_seed(g["trainer"]["seed"])
+    loss = GaussianDiffusionTrainer(net, 1e-4, 0.02, g["cfg"]["T"])(g["x"], g["trainer"]["labels"])
+    assert _rel(loss.detach(), g["trainer"]["loss"]) < 1e-4
+    net.eval()
+    s = g["sampler"]
+    torch.manual_seed(s["seed"])
+    xT = torch.randn(2, 3, 16, 16)          # the fixture drew x_T after seeding (oracle/make_golden.py)
+    assert torch.equal(xT, s["xT"])
+    x0 = GaussianDiffusionSampler(net, 1e-4, 0.02, s["T"], w=s["w"])(xT, s["labels"])
+    assert float((x0 - s["x0"]).abs().max()) < 1e-4
+
+
+def test_identity_denoiser_matches_golden(golden_dir):
+    g = _load(golden_dir, "diffusion_identity.pt")
+
+    class Id(torch.nn.Module):
+        def forward(self, x, t, labels=None):
+            return x[:, :3]
+
+    torch.manual_seed(0)
+    x = torch.rand(2, 3, 4, 4) * 2 - 1
+    assert torch.equal(x, g["trainer_x0"])
+    loss = GaussianDiffusionTrainer(Id(), 1e-4, 0.02, 1000)(x, torch.tensor([1, 2]))
+    assert torch.allclose(loss, g["trainer_loss"], atol=1e-6)
+    torch.manual_seed(1)
+    xT = torch.randn(2, 3, 4, 4)
+    x0 = GaussianDiffusionSampler(Id(), 1e-4, 0.02, 10, w=1.8)(xT, torch.tensor([1, 2]))
+    assert torch.allclose(x0, g["sampler_x0"], atol=1e-5)
+
+
+def test_wider_topology_vs_oracle():
+    """Three levels, two res blocks, attention at level 1, concat widths that straddle GroupNorm groups."""
+    cfg = dict(T=50, ch=32, ch_mult=[1, 2, 2], attn=[1], num_res_blocks=2, dropout=0.0)
+    torch.manual_seed(3)
+    ref = R.UNet(num_labels=5, **cfg)
+    net = UNetC(num_labels=5, compute_dtype=torch.float32, **cfg)
+    net.load_state_dict(ref.state_dict())
+    x = torch.randn(2, 3, 16, 16)
+    t = torch.tensor([1, 40])
+    lab = torch.tensor([3, 0])
+    e_ref = ref(x, t, lab)
+    e = net(x, t, lab)
+    assert _rel(e.detach(), e_ref.detach()) < 2e-5
+    gy = torch.randn_like(e_ref)
+    e_ref.backward(gy)
+    e.backward(gy)
+    pr = dict(ref.named_parameters())
+    for k, p in net.named_parameters():
+        if pr[k].grad is None:
+            continue
+        assert _close(p.grad, pr[k].grad, 2e-4), (k, _rel(p.grad, pr[k].grad))
+
+
+def test_second_backward_without_zero_grad_accumulates():
+    cfg = dict(T=20, ch=32, ch_mult=[1, 1], attn=[], num_res_blocks=1, dropout=0.0)
+    torch.manual_seed(5)
+    net = UNetU(compute_dtype=torch.float32, **cfg)
+    x = torch.randn(1, 3, 8, 8)
+    t = torch.tensor([4])
+    net(x, t).sum().backward()
+    g1 = net.head.weight.grad.clone()
+    net(x, t).sum().backward()
+    assert torch.allclose(net.head.weight.grad, 2 * g1, rtol=1e-5, atol=1e-7)
