@@ -39,7 +39,7 @@ PROTOTYPES = {
     "hd_conv_tc_supported": [I, I, I, I, I, I, I, I],
     "hd_wgrad_tc": [P, I, P, I, I, P, I, I, P, P, L, I, I, I, I, P],
     "hd_wgrad_tc_supported": [I, I, I, I, I, I, I, I],
-    "hd_wgrad_tc_workspace": [I, I, I, I, I, I, I, I],
+    "hd_wgrad_tc_workspace": [I, I, I, I, I, I, I, I, I],
     "hd_attn_fwd_tc": [P, P, P, I, I, I, P],
     "hd_attn_bwd_tc": [P, P, P, P, P, P, I, I, I, P],
     "hd_attn_tc_supported": [I, I],

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhdiff_b200.so")
 SOURCES = ["hd_simt.cu", "hd_fused.cu", "hd_conv_tc.cu", "hd_attn_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
 
 def _stale(obj, deps):

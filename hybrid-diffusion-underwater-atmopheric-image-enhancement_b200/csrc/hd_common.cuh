@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #define HD_OK 0
 #define HD_ERR_ARG (-1)       // bad shape / alignment / null pointer

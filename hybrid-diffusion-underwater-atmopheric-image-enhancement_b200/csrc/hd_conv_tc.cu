@@ -1,0 +1,288 @@
+// K1/K2: implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), bf16 in,
+// fp32 accumulate.  One kernel covers every convolution of the path except the 3-channel head/tail:
+//   * 3x3 and 1x1 stride-1 convolutions (ResBlock conv1/conv2, shortcut, AttnBlock q/k/v/proj, UpSample.c)
+//       reference: nn.Conv2d call sites DiffusionFreeGuidence/ModelCondition.py:82,96-99,130,144,147
+//   * DownSample's conv3x3 s2 + conv5x5 s2 (ModelCondition.py:71-76) and UpSample's ConvTranspose2d 5x5 s2
+//       (ModelCondition.py:83) as stride-1 3x3 convolutions on 2x2 space-to-depth views
+//   * the skip concatenation torch.cat([h, skip]) (ModelCondition.py:271) as a K-split over two sources
+//   * every data gradient (dgrad) = the same kernel on flipped / transposed packed weights
+// GEMM view: M = output pixels (tile of 128 = TH x TW patch of one image), N = output channels, K = taps x Cin.
+// A tiles are TMA boxes of the NHWC activation tensor shifted by the tap offset (out-of-bounds = zero
+// padding); B tiles are TMA boxes of the packed K-major weights.  Accumulators live in TMEM (two buffers,
+// so the epilogue of tile i overlaps the main loop of tile i+1).  Epilogue: + bias + per-sample embedding
+// + residual, bf16 store.
+#include "hd_tc_common.cuh"
+#include <mutex>
+
+namespace {
+
+constexpr int kThreads = 192;          // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kABytes = 128 * 128;     // 128 pixels x 64 bf16
+constexpr int kMaxStages = 8;
+
+struct ConvTcParams {
+    int N, H, W, TH, TW, tiles_x, tiles_y, m_tiles, n_tiles, NT;
+    int k, pad, P_in, nchunk0, nchunk_c, kblocks, stages;
+    int Cout, P_out;
+    const float* bias; const float* emb; long long emb_stride;
+    const __nv_bfloat16* res; __nv_bfloat16* out;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapB, const ConvTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = p.NT * 128;
+    const int stage_bytes = kABytes + b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                       // [stages]
+    uint64_t* empty = bars + kMaxStages;         // [stages]
+    uint64_t* tfull = bars + 2 * kMaxStages;     // [2]
+    uint64_t* tempty = bars + 2 * kMaxStages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+                const int tx_i = m_tile % p.tiles_x; const int r = m_tile / p.tiles_x;
+                const int ty_i = r % p.tiles_y; const int n = r / p.tiles_y;
+                const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                    const int cc = kb % p.nchunk_c; const int r2 = kb / p.nchunk_c;
+                    const int py = r2 % p.P_in; const int tap = r2 / p.P_in;
+                    const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    if (cc < p.nchunk0) tma_load_5d(sa, &mapA0, &full[stage], cc * 64, x0 + dx, py, y0 + dy, n);
+                    else tma_load_5d(sa, &mapA1, &full[stage], (cc - p.nchunk0) * 64, x0 + dx, py, y0 + dy, n);
+                    tma_load_2d(sa + kABytes, &mapB, &full[stage], kb * 64, n_tile * p.NT);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
+            int stage = 0; uint32_t phase = 0; int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
+                    const uint64_t bdesc = umma_smem_desc(sa + kABytes, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)      // 4 x (K = 16): advance 32 bytes inside the 128-byte swizzle atom
+                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+        const int row = quarter * 32 + lane;
+        const int ty = row / p.TW, tx = row % p.TW;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+            const int tx_i = m_tile % p.tiles_x; const int r = m_tile / p.tiles_x;
+            const int ty_i = r % p.tiles_y; const int n = r / p.tiles_y;
+            const int y = ty_i * p.TH + ty, x = tx_i * p.TW + tx;
+            const bool valid = y < p.H;
+            mbar_wait(&tfull[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
+            const float* emb_row = p.emb ? p.emb + (long long)n * p.emb_stride : nullptr;
+            for (int c = 0; c < p.NT; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c, v);
+                tmem_wait_ld();
+                if (valid) {
+                    const int j = n_tile * p.NT + c;            // logical output channel of v[0]
+                    long long off;
+                    if (p.P_out == 1) {
+                        off = (((long long)n * p.H + y) * p.W + x) * p.Cout + j;
+                    } else {
+                        const int q = j / p.Cout, cph = j - q * p.Cout;
+                        off = (((long long)n * (2 * p.H) + (2 * y + (q >> 1))) * (2 * p.W) + (2 * x + (q & 1))) * p.Cout + cph;
+                    }
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + j + i);
+                    }
+                    if (emb_row) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] += __ldg(emb_row + j + i);
+                    }
+                    if (p.res) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
+                        uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+                        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float2 a = __bfloat1622float2(h0[i]), b = __bfloat1622float2(h1[i]);
+                            f[2 * i] += a.x; f[2 * i + 1] += a.y; f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
+                        }
+                    }
+                    uint4 o0, o1;
+                    o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+                    o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                    uint4* op = reinterpret_cast<uint4*>(p.out + off);
+                    op[0] = o0; op[1] = o1;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+int pick_nt(int CoutL) {
+    if (CoutL <= 256) return (CoutL % 16 == 0) ? CoutL : 0;
+    for (int nt = 256; nt >= 64; nt -= 64)
+        if (CoutL % nt == 0) return nt;
+    return 0;
+}
+
+bool conv_geometry(int H, int W, int* TH, int* TW) {
+    int tw = W < 128 ? W : 128;
+    if (tw < 8 || 128 % tw != 0 || W % tw != 0) return false;
+    int th = 128 / tw;
+    if (th > H) return false;
+    *TH = th; *TW = tw;
+    return true;
+}
+
+}  // namespace
+
+// ---- host: tensor map helpers (shared with the other tcgen05 translation units) ----
+hd_encode_tiled_fn hd_get_encode_tiled() {
+    static hd_encode_tiled_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<hd_encode_tiled_fn>(sym);
+    });
+    return fn;
+}
+
+int hd_make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box) {
+    hd_encode_tiled_fn enc = hd_get_encode_tiled();
+    if (!enc) { hd_set_error("cuTensorMapEncodeTiled entry point unavailable"); return HD_ERR_DRIVER; }
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_elems[i - 1] * 2;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        static char buf[256];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u", (int)r, rank,
+                 (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+        hd_set_error(buf);
+        return HD_ERR_DRIVER;
+    }
+    return HD_OK;
+}
+
+// NHWC activation view [N][P*H][P*W][C] as the 5-d tensor (Cv = P*C, W, P, H, N); box = 64 channels x TW x 1 x TH x 1
+int hd_make_act_tmap(CUtensorMap* m, const void* base, int C, int P, int N, int H, int W, int box_c, int TW, int TH) {
+    uint64_t dims[5] = {(uint64_t)P * C, (uint64_t)W, (uint64_t)P, (uint64_t)H, (uint64_t)N};
+    uint64_t PW = (uint64_t)P * W, PH = (uint64_t)P * H;
+    uint64_t str[4] = {(uint64_t)P * C, PW * C, (uint64_t)P * PW * C, PH * PW * C};
+    uint32_t box[5] = {(uint32_t)box_c, (uint32_t)TW, 1, (uint32_t)TH, 1};
+    return hd_make_tmap_bf16(m, base, 5, dims, str, box);
+}
+
+extern "C" int hd_conv_tc_supported(int C0, int C1, int P_in, int Cout, int P_out, int H, int W, int k) {
+    if (k != 1 && k != 3) return 0;
+    if (C0 <= 0 || C0 % 64 != 0 || C1 % 64 != 0) return 0;
+    if (!(P_in == 1 || (P_in == 2 && C1 == 0))) return 0;
+    if (!(P_out == 1 || P_out == 2)) return 0;
+    if (Cout % 16 != 0) return 0;
+    if (pick_nt(Cout * P_out * P_out) == 0) return 0;
+    int TH, TW;
+    return conv_geometry(H, W, &TH, &TW) ? 1 : 0;
+}
+
+extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int P_in, const void* w, const float* bias,
+                          const float* emb, int64_t emb_stride, const void* res, void* out, int Cout, int P_out,
+                          int N, int H, int W, int ksize, cudaStream_t stream) {
+    HD_REQUIRE(in0 && w && out && N > 0);
+    if (!hd_conv_tc_supported(C0, C1, P_in, Cout, P_out, H, W, ksize)) { hd_set_error("hd_conv_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
+    HD_REQUIRE(P_out == 1 || !emb);
+    ConvTcParams p{};
+    p.N = N; p.H = H; p.W = W;
+    conv_geometry(H, W, &p.TH, &p.TW);
+    p.tiles_x = W / p.TW; p.tiles_y = (H + p.TH - 1) / p.TH;
+    p.m_tiles = N * p.tiles_x * p.tiles_y;
+    const int CoutL = Cout * P_out * P_out;
+    p.NT = pick_nt(CoutL); p.n_tiles = CoutL / p.NT;
+    p.k = ksize; p.pad = ksize / 2; p.P_in = P_in;
+    if (P_in == 1) { p.nchunk0 = C0 / 64; p.nchunk_c = (C0 + C1) / 64; }
+    else { p.nchunk0 = 2 * C0 / 64; p.nchunk_c = p.nchunk0; }
+    p.kblocks = ksize * ksize * P_in * p.nchunk_c;
+    const int CinL = (C0 + C1) * P_in * P_in;
+    const int stage_bytes = kABytes + p.NT * 128;
+    p.stages = (200 * 1024) / stage_bytes; if (p.stages > kMaxStages) p.stages = kMaxStages;
+    p.Cout = Cout; p.P_out = P_out;
+    p.bias = bias; p.emb = emb; p.emb_stride = emb_stride;
+    p.res = (const __nv_bfloat16*)res; p.out = (__nv_bfloat16*)out;
+
+    CUtensorMap mA0, mA1, mB;
+    int rc = hd_make_act_tmap(&mA0, in0, C0, P_in, N, H, W, 64, p.TW, p.TH); if (rc) return rc;
+    if (C1 > 0) { rc = hd_make_act_tmap(&mA1, in1, C1, 1, N, H, W, 64, p.TW, p.TH); if (rc) return rc; }
+    else mA1 = mA0;
+    {
+        uint64_t dims[2] = {(uint64_t)ksize * ksize * CinL, (uint64_t)CoutL};
+        uint64_t str[1] = {(uint64_t)ksize * ksize * CinL};
+        uint32_t box[2] = {64, (uint32_t)p.NT};
+        rc = hd_make_tmap_bf16(&mB, w, 2, dims, str, box); if (rc) return rc;
+    }
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(conv_tc_kernel)"); return HD_ERR_CUDA; }
+        attr_set = true;
+    }
+    int grid = p.m_tiles * p.n_tiles; const int sms = hd_num_sms(); if (grid > sms) grid = sms;
+    conv_tc_kernel<<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}

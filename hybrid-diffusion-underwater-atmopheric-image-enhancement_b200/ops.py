@@ -69,7 +69,7 @@ class CudaOps:
         lib = self.lib
         if (self.use_tc and dt == BF16 and not in_nchw and not dy_nchw
                 and lib.hd_wgrad_tc_supported(C0, C1, P_in, Cdy, P_dy, H, W, k)):
-            need = lib.hd_wgrad_tc_workspace(C0, C1, P_in, Cdy, P_dy, N * H * W, W, k)
+            need = lib.hd_wgrad_tc_workspace(C0, C1, P_in, Cdy, P_dy, N, H, W, k)
             if workspace is None or workspace.numel() * 4 < need:
                 workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=dw.device)
             rc = lib.hd_wgrad_tc(_p(x0), C0, _p(x1), C1, P_in, _p(dy), Cdy, P_dy, _p(dw), _p(workspace),

@@ -1,0 +1,117 @@
+/* hdiff_b200 — C ABI of the B200-native DDPM / classifier-free-guidance hot path.
+ *
+ * The reference (gusanagy/Hybrid-Diffusion-Underwater-Atmopheric-Image-Enhancement) has no FFI: its
+ * boundary is the Python class API.  The Python host package mirrors that API and
+ * lowers it onto the entry points below, which are what a maintainer binds (ctypes stub in
+ * INTEGRATION.md).  Conventions:
+ *   - plain pointers and sizes only; device pointers are owned by the caller; kernels never allocate,
+ *     free or retain them; scratch is passed in;
+ *   - every launch goes on the `stream` argument (a cudaStream_t passed as void*);
+ *   - return 0 on success, negative on error (HD_ERR_*); `hd_last_error()` holds the message;
+ *   - `dtype`: 0 = fp32 activations ("fp32 check mode"), 1 = bf16 activations (fp32 accumulate).
+ *   - activations are NHWC; a view argument P in {1,2} exposes a tensor through its 2x2
+ *     space-to-depth rearrangement ([N][2H][2W][C] seen as [N][H][W][4C], channel = (py*2+px)*C + c).
+ * Reference line numbers are relative to the reference repository root.
+ */
+#ifndef HDIFF_B200_H
+#define HDIFF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HD_OK 0
+#define HD_ERR_ARG (-1)
+#define HD_ERR_UNSUPPORTED (-2)
+#define HD_ERR_CUDA (-3)
+#define HD_ERR_DRIVER (-4)
+
+typedef void* hd_stream_t;
+
+const char* hd_last_error(void);
+int hd_abi_version(void);
+
+/* ---- convolutions: nn.Conv2d / nn.ConvTranspose2d call sites DiffusionFreeGuidence/ModelCondition.py:71-72,
+ *      82-83,96-99,130,144,147,219,251 and torch.cat :271; backward = autograd of the same (TrainCondition.py:60).
+ *      Logical stride-1 'same' convolution, ksize in {1,3}, on views; w = packed [CoutL][ksize^2][CinL]. ---- */
+int hd_conv_simt(int dtype, const void* in0, int C0, const void* in1, int C1, int P_in, int in_nchw_f32,
+                 const void* w, const float* bias, const float* emb, int64_t emb_stride, const void* res,
+                 void* out, int Cout, int P_out, int out_nchw_f32, int N, int H, int W, int ksize, hd_stream_t stream);
+int hd_wgrad_simt(int dtype, const void* in0, int C0, const void* in1, int C1, int P_in, int in_nchw_f32,
+                  const void* dy, int Cdy, int P_dy, int dy_nchw_f32, float* dw, int N, int H, int W, int ksize,
+                  hd_stream_t stream);
+/* tcgen05 / TMEM / TMA implicit GEMM, bf16 (K1 forward, K2 data gradient through flipped packed weights) */
+int hd_conv_tc_supported(int C0, int C1, int P_in, int Cout, int P_out, int H, int W, int ksize);
+int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int P_in, const void* w, const float* bias,
+               const float* emb, int64_t emb_stride, const void* res, void* out, int Cout, int P_out,
+               int N, int H, int W, int ksize, hd_stream_t stream);
+/* K3 weight gradient: split over pixels, fp32 partials in `workspace`, deterministic second-stage reduce */
+int hd_wgrad_tc_supported(int C0, int C1, int P_in, int Cdy, int P_dy, int H, int W, int ksize);
+int64_t hd_wgrad_tc_workspace(int C0, int C1, int P_in, int Cdy, int P_dy, int N, int H, int W, int ksize);
+int hd_wgrad_tc(const void* in0, int C0, const void* in1, int C1, int P_in, const void* dy, int Cdy, int P_dy,
+                float* dw, void* workspace, int64_t workspace_bytes, int N, int H, int W, int ksize, hd_stream_t stream);
+
+/* ---- AttnBlock core: softmax(q k^T C^-1/2) v, single head, head_dim = C (ModelCondition.py:101-120).
+ *      qkv = [N][S][3C] (q | k | v), out/dout = [N][S][C], lse/delta = [N][S] fp32. ---- */
+int hd_attn_fwd_simt(int dtype, const void* qkv, void* out, float* lse, int N, int S, int C, hd_stream_t stream);
+int hd_attn_bwd_simt(int dtype, const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                     void* dqkv, int N, int S, int C, hd_stream_t stream);
+int hd_attn_tc_supported(int S, int C);
+int hd_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int S, int C, hd_stream_t stream);
+int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                   int N, int S, int C, hd_stream_t stream);
+
+/* ---- GroupNorm(32) + Swish (+ Dropout): ModelCondition.py:128-129,141-143,95,249-250.  Two-source input
+ *      (C0 | C1 channels) fuses torch.cat :271 into the normalisation.  sums/gsums = [N][G][2] fp64. ---- */
+int hd_gn_stats(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, double* sums,
+                hd_stream_t stream);
+int hd_gn_apply(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, const double* sums,
+                const float* gamma, const float* beta, float eps, int act, float p_drop, uint64_t seed, void* out,
+                hd_stream_t stream);
+int hd_gn_bwd_reduce(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G,
+                     const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
+                     uint64_t seed, const void* dy, double* gsums, float* dgamma, float* dbeta, hd_stream_t stream);
+int hd_gn_bwd_apply(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G,
+                    const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
+                    uint64_t seed, const void* dy, const double* gsums, const void* add, const void* acc0,
+                    const void* acc1, void* dx0, void* dx1, hd_stream_t stream);
+/* bias / embedding-add gradients: per-sample and total column sums (both accumulate) */
+int hd_colsum(int dtype, const void* t, int nchw_f32, int N, int64_t HW, int C, float* per_n, int64_t ld_per_n,
+              float* total, hd_stream_t stream);
+
+/* ---- embedding path, fp32: TimeEmbedding / ConditionalEmbedding / temb_proj / cond_proj
+ *      (ModelCondition.py:27-65,132-139,158-159) ---- */
+int hd_linear_fwd(const float* x, int M, int K, int64_t ldx, const float* w, const float* b, float* y, int Nout,
+                  int64_t ldy, int in_swish, int accumulate, hd_stream_t stream);
+int hd_linear_bwd_x(const float* dy, int M, int Nout, int64_t lddy, const float* w, int K, const float* x_pre,
+                    int64_t ldx, float* dx, int64_t lddx, int accumulate, hd_stream_t stream);
+int hd_linear_bwd_w(const float* dy, int M, int Nout, int64_t lddy, const float* x, int K, int64_t ldx, int in_swish,
+                    float* dw, float* db, hd_stream_t stream);
+int hd_embedding_fwd(const float* table, int rows, int dim, const int64_t* idx, int M, float* out, hd_stream_t stream);
+int hd_embedding_bwd(const float* dout, int dim, const int64_t* idx, int M, float* dtable, int64_t padding_idx,
+                     hd_stream_t stream);
+
+/* ---- parameter layouts: OIHW / IOHW fp32 masters <-> packed GEMM operands ---- */
+int hd_gather_pack(int out_dtype, const float* src, const int32_t* ia, const int32_t* ib, int64_t n, void* out,
+                   hd_stream_t stream);
+int hd_scatter_unpack(const float* packed, const int32_t* inv, int64_t n, float* dst, hd_stream_t stream);
+
+/* ---- diffusion process: extract / q_sample / mse_loss (DiffusionCondition.py:9-16,41-45) and one sampler step
+ *      p_mean_variance + CFG mix + noise + NaN check + final clip (DiffusionCondition.py:68-98) ---- */
+int hd_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ab, const float* sqrt_1m_ab,
+                float* xt, int N, int64_t chw, hd_stream_t stream);
+int hd_mse_fwd(const float* pred, const float* noise, float* loss, int64_t n, hd_stream_t stream);
+int hd_mse_bwd(const float* pred, const float* noise, const float* g, float* dpred, int64_t n, hd_stream_t stream);
+int hd_sampler_step(float* x, const float* eps_c, const float* eps_u, const float* z, float w1, float w, const float* coef,
+                    const int* step_ptr, int last_step_clip, int* nan_flag, int64_t n, hd_stream_t stream);
+int hd_add_int(int* p, int delta, hd_stream_t stream);
+
+/* ---- clip_grad_norm_ + AdamW on the flat buffers (TrainCondition.py:39,61-63) ---- */
+int hd_sqnorm(const float* g, int64_t n, double* out, hd_stream_t stream);
+int hd_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const double* sqnorm, float max_norm, float lr,
+                  float b1, float b2, float eps, float wd, int step, hd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,176 @@
+"""GPU parity tests, model level: the CUDA path through the reference-shaped Python API against
+  (1) golden fixtures minted from the reference itself (tests/golden, oracle/make_golden.py), and
+  (2) the oracle (oracle/ref_torch.py) run in fp32 on the same GPU with TF32 disabled,
+on identical weights, seeds and inputs.  Tolerances (BASELINE.json north_star): relative error <= 1e-2 in
+bf16, 1e-5-class in the fp32 check mode (the checks below allow a small multiple for accumulated depth)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_torch as R
+
+
+@pytest.fixture(autouse=True)
+def _cuda_backend():
+    import hdiff_b200.ops as hops
+    hops.set_backend(None)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _close(a, b, rtol, atol):
+    return float((a.double() - b.double()).norm()) <= rtol * float(b.double().norm()) + atol
+
+
+def _nets(cfg, num_labels, dtype, dev, sd=None, seed=0):
+    from hdiff_b200.diffusion.Model import UNet as UNetU
+    from hdiff_b200.DiffusionFreeGuidence.ModelCondition import UNet as UNetC
+    torch.manual_seed(seed)
+    ref = R.UNet(num_labels=num_labels, **cfg)
+    if sd is not None:
+        ref.load_state_dict(sd)
+    net = UNetU(compute_dtype=dtype, **cfg) if num_labels is None else UNetC(num_labels=num_labels, compute_dtype=dtype, **cfg)
+    net.load_state_dict(ref.state_dict())
+    return net.to(dev), ref.to(dev)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("tag", ["cond", "uncond"])
+def test_unet_tiny_vs_reference_golden(golden_dir, dtype, tol, tag):
+    g = _load(golden_dir, "unet_tiny.pt")
+    dev = torch.device("cuda")
+    sd = g["sd"] if tag == "cond" else {k: v for k, v in g["sd"].items() if not k.startswith("cond_embedding.")}
+    net, _ = _nets(g["cfg"], 10 if tag == "cond" else None, dtype, dev, sd=sd)
+    net.train()
+    rec = g[tag]
+    x, t = g["x"].to(dev), g["t"].to(dev)
+    eps = net(x, t) if rec["labels"] is None else net(x, t, rec["labels"].to(dev))
+    assert _rel(eps.detach().cpu(), rec["eps"]) < tol
+    (eps ** 2).sum().backward()
+    params = dict(net.named_parameters())
+    gscale = max(float(v.norm()) for v in rec["grads"].values())
+    for k, gref in rec["grads"].items():
+        assert params[k].grad is not None, k
+        assert _close(params[k].grad.cpu(), gref, 4 * tol, 1e-3 * tol * gscale + 2e-5), (k, _rel(params[k].grad.cpu(), gref))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+def test_trainer_and_cfg_sampler_vs_reference_golden(golden_dir, dtype, tol):
+    from hdiff_b200.DiffusionFreeGuidence.DiffusionCondition import GaussianDiffusionTrainer, GaussianDiffusionSampler
+    g = _load(golden_dir, "unet_tiny.pt")
+    dev = torch.device("cuda")
+    net, ref = _nets(g["cfg"], 10, dtype, dev, sd=g["sd"])
+    # RNG streams differ between CPU and CUDA generators, so the reference side is the oracle on this GPU
+    x, lab = g["x"].to(dev), g["trainer"]["labels"].to(dev)
+    net.train(); ref.train()
+    torch.manual_seed(21)
+    loss = GaussianDiffusionTrainer(net, 1e-4, 0.02, g["cfg"]["T"]).to(dev)(x, lab)
+    torch.manual_seed(21)
+    rloss = R.GaussianDiffusionTrainer(ref, 1e-4, 0.02, g["cfg"]["T"]).to(dev)(x, lab)
+    assert _rel(loss, rloss) < tol
+    net.eval(); ref.eval()
+    s = g["sampler"]
+    xT = s["xT"].to(dev)
+    torch.manual_seed(22)
+    x0 = GaussianDiffusionSampler(net, 1e-4, 0.02, s["T"], w=s["w"]).to(dev)(xT, s["labels"].to(dev))
+    torch.manual_seed(22)
+    with torch.no_grad():
+        r0 = R.GaussianDiffusionSampler(ref, 1e-4, 0.02, s["T"], w=s["w"]).to(dev)(xT, s["labels"].to(dev))
+    assert float((x0 - r0).abs().max()) < (1e-4 if dtype == torch.float32 else 0.1)
+    assert float(x0.abs().max()) <= 1.0
+
+
+def test_identity_denoiser_kat():
+    """SURVEY.md §8(c) known answer: pins RNG order randint -> randn_like and the q_sample / MSE arithmetic."""
+    from hdiff_b200.DiffusionFreeGuidence.DiffusionCondition import GaussianDiffusionTrainer, GaussianDiffusionSampler
+    dev = torch.device("cuda")
+
+    class Id(torch.nn.Module):
+        def forward(self, x, t, labels=None):
+            return x[:, :3]
+
+    x = (torch.rand(2, 3, 4, 4) * 2 - 1).to(dev)
+    lab = torch.tensor([1, 2], device=dev)
+    torch.manual_seed(0)
+    loss = GaussianDiffusionTrainer(Id(), 1e-4, 0.02, 1000).to(dev)(x, lab)
+    torch.manual_seed(0)
+    rloss = R.GaussianDiffusionTrainer(Id(), 1e-4, 0.02, 1000).to(dev)(x, lab)
+    assert torch.allclose(loss, rloss, rtol=1e-6, atol=1e-6)
+    xT = torch.randn(2, 3, 4, 4, device=dev)
+    torch.manual_seed(1)
+    a = GaussianDiffusionSampler(Id(), 1e-4, 0.02, 10, w=1.8).to(dev)(xT, lab)
+    torch.manual_seed(1)
+    b = R.GaussianDiffusionSampler(Id(), 1e-4, 0.02, 10, w=1.8).to(dev)(xT, lab)
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+def test_cfg1_shape_unet_vs_oracle(dtype, tol):
+    """BASELINE.json configs[0] network (ch=64, ch_mult=[1,2,2,2], attn=[1], 2 res blocks) at 64x64, batch 2:
+    forward and every parameter gradient against the oracle; exercises the tcgen05 kernels in bf16."""
+    import hdiff_b200.ops as hops
+    dev = torch.device("cuda")
+    cfg = dict(T=1000, ch=64, ch_mult=[1, 2, 2, 2], attn=[1], num_res_blocks=2, dropout=0.0)
+    net, ref = _nets(cfg, 10, dtype, dev, seed=11)
+    net.train(); ref.train()
+    torch.manual_seed(12)
+    x = torch.rand(2, 3, 64, 64, device=dev) * 2 - 1
+    t = torch.tensor([5, 700], device=dev)
+    lab = torch.tensor([0, 7], device=dev)
+    before = hops.get().tc_launches
+    e = net(x, t, lab)
+    er = ref(x, t, lab)
+    assert _rel(e.detach(), er.detach()) < tol, _rel(e.detach(), er.detach())
+    gy = torch.randn_like(er)
+    e.backward(gy)
+    er.backward(gy)
+    if dtype == torch.bfloat16:
+        assert hops.get().tc_launches > before, "bf16 mode must run the tcgen05 kernels"
+    pr = dict(ref.named_parameters())
+    gscale = max(float(p.grad.norm()) for p in pr.values() if p.grad is not None)
+    worst = ("", 0.0)
+    for k, p in net.named_parameters():
+        if pr[k].grad is None:
+            continue
+        r = _rel(p.grad, pr[k].grad)
+        if not _close(p.grad, pr[k].grad, 4 * tol, 2e-3 * tol * gscale + 2e-5) and r > worst[1]:
+            worst = (k, r)
+    assert worst[0] == "", worst
+
+
+def test_training_loss_curve_tracks_oracle():
+    """20 optimisation steps (clip 1.0 + AdamW) from identical weights and RNG seeds, dropout 0: the loss curves
+    of the CUDA path (bf16) and the oracle (fp32) stay within 2 % of each other (north_star: 1 % over 200 steps
+    at full size is checked by bench/parity scripts; this is the CI-sized version)."""
+    from hdiff_b200.DiffusionFreeGuidence.DiffusionCondition import GaussianDiffusionTrainer
+    dev = torch.device("cuda")
+    cfg = dict(T=1000, ch=64, ch_mult=[1, 2], attn=[1], num_res_blocks=1, dropout=0.0)
+    net, ref = _nets(cfg, 10, torch.bfloat16, dev, seed=31)
+    tr = GaussianDiffusionTrainer(net, 1e-4, 0.02, 1000).to(dev)
+    rtr = R.GaussianDiffusionTrainer(ref, 1e-4, 0.02, 1000).to(dev)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-4, weight_decay=1e-4)
+    torch.manual_seed(32)
+    x = torch.rand(4, 3, 32, 32, device=dev) * 2 - 1
+    lab = torch.tensor([1, 2, 3, 4], device=dev)
+    mine, theirs = [], []
+    for step in range(20):
+        torch.manual_seed(100 + step)
+        mine.append(float(R.train_step(tr, opt, x, lab)))
+        torch.manual_seed(100 + step)
+        theirs.append(float(R.train_step(rtr, ropt, x, lab)))
+    for a, b in zip(mine, theirs):
+        assert abs(a - b) <= 0.02 * abs(b) + 1e-4, (mine, theirs)
+    assert mine[-1] < mine[0]
