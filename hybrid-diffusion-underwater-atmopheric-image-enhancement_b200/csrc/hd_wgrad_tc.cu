@@ -1,0 +1,251 @@
+// K3: convolution weight gradient on tcgen05 / TMEM / TMA, bf16 in, fp32 accumulate.
+//   dW[co][tap][ci] = sum over pixels of dY(pixel, co) * X(pixel + tap, ci)      (autograd of the nn.Conv2d /
+//   nn.ConvTranspose2d call sites DiffusionFreeGuidence/ModelCondition.py:71-72,82-83,96-99,130,144,147)
+// GEMM view: the reduction (K) runs over PIXELS, so both operands are "MN-major" in shared memory exactly as
+// TMA delivers NHWC boxes ([pixel rows][64 channels], 128-byte swizzle):
+//   A (M = 128) = two 64-wide blocks of shifted input X, one per (tap, 64-channel chunk)
+//   B (N <= 256) = the dY box, 64-wide blocks of output channels
+//   D[(tap, ci)][co] accumulates in TMEM; a CTA owns `G` such 128-row pairs and a contiguous range of
+//   pixel tiles (split-K over pixels).  Partials go to an fp32 workspace [split][rows][N]; a second kernel
+//   sums them in a fixed order (deterministic) and writes the packed [co][tap][ci] gradient.
+#include "hd_tc_common.cuh"
+
+int hd_make_act_tmap(CUtensorMap* m, const void* base, int C, int P, int N, int H, int W, int box_c, int TW, int TH);
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBlkBytes = 64 * 128;    // one [64 pixels][64 channels] bf16 box
+constexpr int kMaxStages = 8;
+
+struct WgradTcParams {
+    int N, H, W, TH, TW, tiles_x, tiles_y, pix_tiles, tiles_per_split, splits;
+    int k, pad, P_in, nchunk0, nchunk_c;      // input side chunking (as in hd_conv_tc)
+    int nblocks;                              // kk * P_in * nchunk_c  (64-row blocks of D)
+    int G;                                    // 128-row pairs per CTA
+    int ngroups;
+    int NT, n_tiles, nb;                      // output-channel tile (<= 256), tiles, nb = NT / 64
+    int nch_dy, P_dy;                         // 64-channel chunks per parity row of dY view
+    int stages;
+    float* ws;                                // [splits][nblocks_padded * 64][CoutL]
+    int rows_padded, CoutL;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
+                const __grid_constant__ CUtensorMap mapDY, const WgradTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = p.G * 2 * kBlkBytes, b_bytes = p.nb * kBlkBytes;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kMaxStages;
+    uint64_t* tfull = bars + 2 * kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = blockIdx.x, split = blockIdx.y, n_tile = blockIdx.z;
+    const int t_begin = split * p.tiles_per_split;
+    int t_end = t_begin + p.tiles_per_split; if (t_end > p.pix_tiles) t_end = p.pix_tiles;
+    const int nsteps = t_end - t_begin;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapX0); tma_prefetch_desc(&mapX1); tma_prefetch_desc(&mapDY);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const int tx_i = t % p.tiles_x; const int r = t / p.tiles_x;
+                const int ty_i = r % p.tiles_y; const int n = r / p.tiles_y;
+                const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                for (int b = 0; b < 2 * p.G; ++b) {
+                    int blk = group * 2 * p.G + b;
+                    if (blk >= p.nblocks) blk = p.nblocks - 1;           // padding rows: duplicate, discarded later
+                    const int cc = blk % p.nchunk_c; const int r2 = blk / p.nchunk_c;
+                    const int py = r2 % p.P_in; const int tap = r2 / p.P_in;
+                    const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
+                    if (cc < p.nchunk0) tma_load_5d(sa + b * kBlkBytes, &mapX0, &full[stage], cc * 64, x0 + dx, py, y0 + dy, n);
+                    else tma_load_5d(sa + b * kBlkBytes, &mapX1, &full[stage], (cc - p.nchunk0) * 64, x0 + dx, py, y0 + dy, n);
+                }
+                for (int b = 0; b < p.nb; ++b) {
+                    const int blk = n_tile * p.nb + b;
+                    const int cc = blk % p.nch_dy, py = blk / p.nch_dy;
+                    tma_load_5d(sa + a_bytes + b * kBlkBytes, &mapDY, &full[stage], cc * 64, x0, py, y0, n);
+                }
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.NT, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (int s = 0; s < nsteps; ++s) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sb = sa + a_bytes;
+                for (int g = 0; g < p.G; ++g) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {    // K = 16 pixels = 2 groups of 8 rows = 2048 bytes
+                        const uint64_t adesc = umma_smem_desc(sa + g * 2 * kBlkBytes + k * 2048, kBlkBytes, 1024);
+                        const uint64_t bdesc = umma_smem_desc(sb + k * 2048, kBlkBytes, 1024);
+                        umma_bf16(tmem_base + g * p.NT, adesc, bdesc, idesc, (s | k) != 0);
+                    }
+                }
+                umma_commit(&empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        if (nsteps > 0) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+        }
+        for (int g = 0; g < p.G; ++g) {
+            const int R = (group * p.G + g) * 128 + row;               // row of D: block = R / 64
+            float* dst = p.ws + ((size_t)split * p.rows_padded + R) * p.CoutL + (size_t)n_tile * p.NT;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + g * p.NT;
+            for (int c = 0; c < p.NT; c += 16) {
+                uint32_t v[16];
+                if (nsteps > 0) { tmem_ld16(taddr + c, v); tmem_wait_ld(); }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0;
+                }
+                float4* d4 = reinterpret_cast<float4*>(dst + c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// dw[co][tap][ci] = sum_s ws[s][blk * 64 + r][co],  blk = tap * (CinL/64) + ci / 64, r = ci % 64
+__global__ void wgrad_reduce_kernel(const float* ws, int splits, int rows_padded, int rows, int CoutL, int kk, int CinL, float* dw) {
+    const int64_t total = (int64_t)rows * CoutL;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int co = (int)(i % CoutL); const int R = (int)(i / CoutL);
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += ws[((size_t)sp * rows_padded + R) * CoutL + co];
+        const int tap = R / CinL, ci = R - tap * CinL;
+        dw[((int64_t)co * kk + tap) * CinL + ci] = s;
+    }
+}
+
+bool wgrad_geometry(int H, int W, int* TH, int* TW) {
+    int tw = W < 64 ? W : 64;
+    if (tw < 8 || 64 % tw != 0 || W % tw != 0) return false;
+    int th = 64 / tw;
+    if (H % th != 0) return false;
+    *TH = th; *TW = tw;
+    return true;
+}
+int pick_nt_w(int CoutL) {
+    if (CoutL <= 256) return CoutL % 64 == 0 ? CoutL : 0;
+    for (int nt = 256; nt >= 64; nt -= 64) if (CoutL % nt == 0) return nt;
+    return 0;
+}
+
+struct WgradPlan { WgradTcParams p; };
+
+bool make_plan(int C0, int C1, int P_in, int Cdy, int P_dy, int N, int H, int W, int k, WgradTcParams* out) {
+    WgradTcParams p{};
+    if (k != 1 && k != 3) return false;
+    if (C0 <= 0 || C0 % 64 != 0 || C1 % 64 != 0 || Cdy % 64 != 0) return false;
+    if (!(P_in == 1 || (P_in == 2 && C1 == 0))) return false;
+    if (!(P_dy == 1 || P_dy == 2)) return false;
+    if (!wgrad_geometry(H, W, &p.TH, &p.TW)) return false;
+    p.N = N; p.H = H; p.W = W;
+    p.tiles_x = W / p.TW; p.tiles_y = H / p.TH; p.pix_tiles = N * p.tiles_x * p.tiles_y;
+    p.k = k; p.pad = k / 2; p.P_in = P_in;
+    if (P_in == 1) { p.nchunk0 = C0 / 64; p.nchunk_c = (C0 + C1) / 64; }
+    else { p.nchunk0 = 2 * C0 / 64; p.nchunk_c = p.nchunk0; }
+    p.nblocks = k * k * P_in * p.nchunk_c;
+    p.CoutL = Cdy * P_dy * P_dy;
+    p.NT = pick_nt_w(p.CoutL); if (!p.NT) return false;
+    p.n_tiles = p.CoutL / p.NT; p.nb = p.NT / 64;
+    p.nch_dy = P_dy * Cdy / 64; p.P_dy = P_dy;
+    const int npairs = (p.nblocks + 1) / 2;
+    int G = 512 / p.NT; if (G > 4) G = 4; if (G > npairs) G = npairs;
+    // keep at least two stages in shared memory
+    while (G > 1 && 2 * (G * 2 + p.nb) * kBlkBytes > 200 * 1024) --G;
+    p.G = G;
+    p.ngroups = (npairs + G - 1) / G;
+    p.rows_padded = p.ngroups * G * 128;
+    const int stage_bytes = (G * 2 + p.nb) * kBlkBytes;
+    p.stages = (200 * 1024) / stage_bytes; if (p.stages > kMaxStages) p.stages = kMaxStages;
+    if (p.stages < 2) return false;
+    // split-K over pixel tiles: fill the machine about twice
+    const int ctas_per_split = p.ngroups * p.n_tiles;
+    int splits = (2 * 148 + ctas_per_split - 1) / ctas_per_split;
+    if (splits > p.pix_tiles) splits = p.pix_tiles;
+    if (splits < 1) splits = 1;
+    p.tiles_per_split = (p.pix_tiles + splits - 1) / splits;
+    p.splits = (p.pix_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    *out = p;
+    return true;
+}
+
+}  // namespace
+
+extern "C" int hd_wgrad_tc_supported(int C0, int C1, int P_in, int Cdy, int P_dy, int H, int W, int k) {
+    WgradTcParams p;
+    return make_plan(C0, C1, P_in, Cdy, P_dy, 1, H, W, k, &p) ? 1 : 0;
+}
+
+extern "C" long long hd_wgrad_tc_workspace(int C0, int C1, int P_in, int Cdy, int P_dy, int N, int H, int W, int k) {
+    WgradTcParams p;
+    if (!make_plan(C0, C1, P_in, Cdy, P_dy, N, H, W, k, &p)) return 0;
+    return (long long)p.splits * p.rows_padded * p.CoutL * 4;
+}
+
+extern "C" int hd_wgrad_tc(const void* in0, int C0, const void* in1, int C1, int P_in, const void* dy, int Cdy, int P_dy,
+                           float* dw, void* workspace, long long workspace_bytes, int N, int H, int W, int k, cudaStream_t stream) {
+    HD_REQUIRE(in0 && dy && dw && workspace && N > 0);
+    WgradTcParams p;
+    if (!make_plan(C0, C1, P_in, Cdy, P_dy, N, H, W, k, &p)) { hd_set_error("hd_wgrad_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
+    HD_REQUIRE(workspace_bytes >= (long long)p.splits * p.rows_padded * p.CoutL * 4);
+    p.ws = (float*)workspace;
+    CUtensorMap mX0, mX1, mDY;
+    int rc = hd_make_act_tmap(&mX0, in0, C0, P_in, N, H, W, 64, p.TW, p.TH); if (rc) return rc;
+    if (C1 > 0) { rc = hd_make_act_tmap(&mX1, in1, C1, 1, N, H, W, 64, p.TW, p.TH); if (rc) return rc; }
+    else mX1 = mX0;
+    rc = hd_make_act_tmap(&mDY, dy, Cdy, P_dy, N, H, W, 64, p.TW, p.TH); if (rc) return rc;
+    const int stage_bytes = (p.G * 2 + p.nb) * kBlkBytes;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * kMaxStages + 2) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(wgrad_tc_kernel)"); return HD_ERR_CUDA; }
+        attr_set = true;
+    }
+    wgrad_tc_kernel<<<dim3(p.ngroups, p.splits, p.n_tiles), kThreads, smem, stream>>>(mX0, mX1, mDY, p);
+    HD_CHECK_LAUNCH();
+    const int rows = p.nblocks * 64;
+    const int CinL = (C0 + C1) * P_in * P_in;
+    const int64_t total = (int64_t)rows * p.CoutL;
+    int grid = (int)((total + 255) / 256); if (grid > 148 * 8) grid = 148 * 8;
+    wgrad_reduce_kernel<<<grid, 256, 0, stream>>>(p.ws, p.splits, p.rows_padded, rows, p.CoutL, k * k, CinL, dw);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}

@@ -104,7 +104,7 @@ class ResBlock(nn.Module):
 class ConvSpec:
     """One logical stride-1 convolution (k in {1,3}) between views, with its packed weights."""
     __slots__ = ("name", "k", "CinL", "CoutL", "P_in", "P_out", "Cout", "Cin", "w_off", "wd_off", "b_off", "n_w", "has_bias",
-                 "_bias_inv", "_bias_same")
+                 "_bias_inv", "_bias_same", "alg_frac")
 
     def __init__(self, name, k, Cin, Cout, P_in, P_out):
         self.name, self.k, self.Cin, self.Cout, self.P_in, self.P_out = name, k, Cin, Cout, P_in, P_out
@@ -112,6 +112,8 @@ class ConvSpec:
         self.n_w = self.CoutL * k * k * self.CinL
         self.w_off = self.wd_off = self.b_off = -1
         self.has_bias = True
+        # real reference taps / packed taps: DownSample packs 9 + 25 taps into 36 slots, ConvTranspose 25 into 36
+        self.alg_frac = 34.0 / 36.0 if P_in == 2 else (25.0 / 36.0 if P_out == 2 else 1.0)
 
 
 def _tbl_conv(off, Co, Ci, k):
@@ -415,7 +417,7 @@ class UNetBase(nn.Module):
         else:
             out = torch.empty((N, H * P_out, W * P_out, Cout), dtype=self.compute_dtype, device=x0.device)
         ops.conv(x0, x1, P_in, self._wv(st, spec, dgrad), None if dgrad else self._bv(st, spec), emb, res, out, P_out,
-                 N, H, W, spec.k, in_nchw=in_nchw, out_nchw=out_nchw)
+                 N, H, W, spec.k, in_nchw=in_nchw, out_nchw=out_nchw, alg_frac=spec.alg_frac)
         return out
 
     def _wgrad(self, st, spec, x0, x1, dy, in_nchw=False, dy_nchw=False):
@@ -426,7 +428,8 @@ class UNetBase(nn.Module):
         else:
             N, H, W = x0.shape[0], x0.shape[1] // spec.P_in, x0.shape[2] // spec.P_in
         dw = st.gpk[spec.w_off // 2: spec.w_off // 2 + spec.n_w]
-        ops.wgrad(x0, x1, spec.P_in, dy, spec.P_out, dw, N, H, W, spec.k, self.compute_dtype, in_nchw=in_nchw, dy_nchw=dy_nchw)
+        ops.wgrad(x0, x1, spec.P_in, dy, spec.P_out, dw, N, H, W, spec.k, self.compute_dtype, in_nchw=in_nchw, dy_nchw=dy_nchw,
+                  alg_frac=spec.alg_frac)
         if spec.has_bias:
             C = spec.Cout                       # physical channels of dy (bias is per physical channel)
             db = st.gpk[st.n_dw + spec.b_off: st.n_dw + spec.b_off + C]

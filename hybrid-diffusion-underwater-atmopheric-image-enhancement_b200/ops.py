@@ -35,16 +35,36 @@ class CudaOps:
         self.use_tc = True          # tcgen05 kernels where the shape is covered
         self.launches = 0           # kernels launched through this object (bench.py reports it)
         self.tc_launches = 0
+        self.prof = None            # bench.py: dict family -> [(start_event, end_event, work)], CUDA events on the launch stream
+
+    # ---- per-launch device timing for bench.py's roofline (off unless `prof` is a dict) ----
+    def _t0(self):
+        if self.prof is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _t1(self, e0, family, work):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.prof.setdefault(family, []).append((e0, e1, work))
 
     # ---- convolution family -------------------------------------------------------------
-    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False):
+    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0):
         """out = conv_k(view(x0|x1, P_in)) + bias + emb[:, :, None, None] + res, logical stride 1, 'same' padding.
-        w: packed [CoutL][k*k][CinL] in the compute dtype.  H, W are the LOGICAL spatial dims."""
+        w: packed [CoutL][k*k][CinL] in the compute dtype.  H, W are the LOGICAL spatial dims.
+        `alg_frac`: share of the packed taps that are real reference taps (space-to-depth views carry zeros);
+        only used for bench.py's algorithmic-FLOP accounting."""
         dt = _DT[w.dtype]
         C0 = x0.shape[1] if in_nchw else x0.shape[-1]
         C1 = 0 if x1 is None else x1.shape[-1]
         Cout = out.shape[1] if out_nchw else out.shape[-1]
         lib = self.lib
+        e0 = self._t0()
+        flops = 2.0 * N * H * W * (Cout * P_out * P_out) * k * k * ((C0 + C1) * P_in * P_in) * alg_frac
         if (self.use_tc and dt == BF16 and not in_nchw and not out_nchw
                 and lib.hd_conv_tc_supported(C0, C1, P_in, Cout, P_out, H, W, k)):
             rc = lib.hd_conv_tc(_p(x0), C0, _p(x1), C1, P_in, _p(w), _p(bias), _p(emb),
@@ -53,20 +73,24 @@ class CudaOps:
             _lib.check(rc, "hd_conv_tc")
             self.launches += 1
             self.tc_launches += 1
+            self._t1(e0, "conv_tc", flops)
             return
         rc = lib.hd_conv_simt(dt, _p(x0), C0, _p(x1), C1, P_in, int(in_nchw), _p(w), _p(bias), _p(emb),
                               0 if emb is None else emb.stride(0), _p(res), _p(out), Cout, P_out, int(out_nchw),
                               N, H, W, k, _stream())
         _lib.check(rc, "hd_conv_simt")
         self.launches += 1
+        self._t1(e0, "conv_simt", flops)
 
-    def wgrad(self, x0, x1, P_in, dy, P_dy, dw, N, H, W, k, dtype, in_nchw=False, dy_nchw=False, workspace=None):
+    def wgrad(self, x0, x1, P_in, dy, P_dy, dw, N, H, W, k, dtype, in_nchw=False, dy_nchw=False, workspace=None, alg_frac=1.0):
         """dw[CoutL][k*k][CinL] (fp32, overwritten) = sum over pixels of dy (x) shifted input."""
         dt = _DT[dtype]
         C0 = x0.shape[1] if in_nchw else x0.shape[-1]
         C1 = 0 if x1 is None else x1.shape[-1]
         Cdy = dy.shape[1] if dy_nchw else dy.shape[-1]
         lib = self.lib
+        e0 = self._t0()
+        flops = 2.0 * N * H * W * (Cdy * P_dy * P_dy) * k * k * ((C0 + C1) * P_in * P_in) * alg_frac
         if (self.use_tc and dt == BF16 and not in_nchw and not dy_nchw
                 and lib.hd_wgrad_tc_supported(C0, C1, P_in, Cdy, P_dy, H, W, k)):
             need = lib.hd_wgrad_tc_workspace(C0, C1, P_in, Cdy, P_dy, N, H, W, k)
@@ -77,46 +101,59 @@ class CudaOps:
             _lib.check(rc, "hd_wgrad_tc")
             self.launches += 2
             self.tc_launches += 1
+            self._t1(e0, "wgrad_tc", flops)
             return
         rc = lib.hd_wgrad_simt(dt, _p(x0), C0, _p(x1), C1, P_in, int(in_nchw), _p(dy), Cdy, P_dy, int(dy_nchw),
                                _p(dw), N, H, W, k, _stream())
         _lib.check(rc, "hd_wgrad_simt")
         self.launches += 1
+        self._t1(e0, "wgrad_simt", flops)
 
     # ---- attention -----------------------------------------------------------------------
     def attn_fwd(self, qkv, out, lse, N, S, C):
+        e0 = self._t0()
+        tc = self.use_tc and qkv.dtype == torch.bfloat16 and self.lib.hd_attn_tc_supported(S, C)
         if self.use_tc and qkv.dtype == torch.bfloat16 and self.lib.hd_attn_tc_supported(S, C):
             _lib.check(self.lib.hd_attn_fwd_tc(_p(qkv), _p(out), _p(lse), N, S, C, _stream()), "hd_attn_fwd_tc")
             self.tc_launches += 1
         else:
             _lib.check(self.lib.hd_attn_fwd_simt(_DT[qkv.dtype], _p(qkv), _p(out), _p(lse), N, S, C, _stream()), "hd_attn_fwd_simt")
         self.launches += 1
+        self._t1(e0, "attn_fwd_tc" if tc else "attn_fwd_simt", 4.0 * N * S * S * C)
 
     def attn_bwd(self, qkv, out, dout, lse, delta, dqkv, N, S, C):
+        e0 = self._t0()
+        tc = self.use_tc and qkv.dtype == torch.bfloat16 and self.lib.hd_attn_tc_supported(S, C)
         if self.use_tc and qkv.dtype == torch.bfloat16 and self.lib.hd_attn_tc_supported(S, C):
             _lib.check(self.lib.hd_attn_bwd_tc(_p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), N, S, C, _stream()), "hd_attn_bwd_tc")
             self.tc_launches += 2
         else:
             _lib.check(self.lib.hd_attn_bwd_simt(_DT[qkv.dtype], _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), N, S, C, _stream()), "hd_attn_bwd_simt")
         self.launches += 3
+        self._t1(e0, "attn_bwd_tc" if tc else "attn_bwd_simt", 8.0 * N * S * S * C)
 
     # ---- GroupNorm family ----------------------------------------------------------------
     def gn_stats(self, x0, x1, N, HW, G, sums):
+        e0 = self._t0()
         C0, C1 = x0.shape[-1], 0 if x1 is None else x1.shape[-1]
         _lib.check(self.lib.hd_gn_stats(_DT[x0.dtype], _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _stream()), "hd_gn_stats")
         self.launches += 1
+        self._t1(e0, "gn_stats", float(N * HW * (C0 + C1) * x0.element_size()))
 
     def gn_apply(self, x0, x1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, out):
+        e0 = self._t0()
         C0, C1 = x0.shape[-1], 0 if x1 is None else x1.shape[-1]
         _lib.check(self.lib.hd_gn_apply(_DT[x0.dtype], _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _p(gamma), _p(beta),
                                         eps, int(act), float(p_drop), int(seed), _p(out), _stream()), "hd_gn_apply")
         self.launches += 1
+        self._t1(e0, "gn_apply", float(2 * N * HW * (C0 + C1) * x0.element_size()))
 
     def gn_bwd(self, x0, x1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, dy, gsums, dgamma, dbeta,
                add, acc0, acc1, dx0, dx1):
         """dgamma/dbeta accumulate; dx0/dx1 are overwritten with dx (+ add + acc0/acc1)."""
         C0, C1 = x0.shape[-1], 0 if x1 is None else x1.shape[-1]
         dt = _DT[x0.dtype]
+        e0 = self._t0()
         _lib.check(self.lib.hd_gn_bwd_reduce(dt, _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _p(gamma), _p(beta), eps,
                                              int(act), float(p_drop), int(seed), _p(dy), _p(gsums), _p(dgamma), _p(dbeta),
                                              _stream()), "hd_gn_bwd_reduce")
@@ -124,6 +161,8 @@ class CudaOps:
                                             int(act), float(p_drop), int(seed), _p(dy), _p(gsums), _p(add), _p(acc0), _p(acc1),
                                             _p(dx0), _p(dx1), _stream()), "hd_gn_bwd_apply")
         self.launches += 2
+        nt = 5 + (add is not None) + (acc0 is not None)       # x, dy twice; dx once; optional addends
+        self._t1(e0, "gn_bwd", float(nt * N * HW * (C0 + C1) * x0.element_size()))
 
     def colsum(self, t, N, HW, C, per_n, total, nchw=False):
         """per_n[n, c] += sum_pix t ; total[c] += sum_{n,pix} t   (either may be None)."""

@@ -46,7 +46,7 @@ class EmuOps:
         x = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
         return to_logical(x, P_in).permute(0, 3, 1, 2).float()
 
-    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False):
+    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0):
         xin = self._logical_in(x0, x1, P_in, in_nchw)
         CinL = xin.shape[1]
         CoutL = w.numel() // (k * k * CinL)
@@ -63,7 +63,7 @@ class EmuOps:
             out.copy_(y.to(out.dtype))
         self.launches += 1
 
-    def wgrad(self, x0, x1, P_in, dy, P_dy, dw, N, H, W, k, dtype, in_nchw=False, dy_nchw=False, workspace=None):
+    def wgrad(self, x0, x1, P_in, dy, P_dy, dw, N, H, W, k, dtype, in_nchw=False, dy_nchw=False, workspace=None, alg_frac=1.0):
         xin = self._logical_in(x0, x1, P_in, in_nchw)
         g = dy.float() if dy_nchw else to_logical(dy, P_dy).permute(0, 3, 1, 2).float()
         CinL, CoutL = xin.shape[1], g.shape[1]

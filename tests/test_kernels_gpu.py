@@ -10,6 +10,14 @@ pytestmark = pytest.mark.gpu
 from tests.emu_backend import EmuOps, to_logical, from_logical  # torch re-statement used as the checker
 
 
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    # the checker must be true fp32: cuDNN / cuBLAS default to TF32 on this GPU
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
 def _ops():
     import hdiff_b200.ops as hops
     hops.set_backend(None)
