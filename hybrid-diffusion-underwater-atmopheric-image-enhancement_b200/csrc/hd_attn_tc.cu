@@ -1,6 +1,492 @@
-// placeholder until the tcgen05 attention / weight-gradient kernels land: report "not covered" so
-// that the operator layer routes to the CUDA-core kernels.
-#include "hd_common.cuh"
-extern "C" int hd_attn_tc_supported(int S, int C) { return 0; }
-extern "C" int hd_attn_fwd_tc(const void*, void*, float*, int, int, int, cudaStream_t) { hd_set_error("hd_attn_fwd_tc: not built"); return HD_ERR_UNSUPPORTED; }
-extern "C" int hd_attn_bwd_tc(const void*, const void*, const void*, const float*, float*, void*, int, int, int, cudaStream_t) { hd_set_error("hd_attn_bwd_tc: not built"); return HD_ERR_UNSUPPORTED; }
+// K5: AttnBlock's spatial self-attention as a flash-style tcgen05 kernel (single head, head_dim = C = 128).
+//   reference: DiffusionFreeGuidence/ModelCondition.py:101-120 (q,k,v = 1x1 convs; w = softmax(q^T k * C^-1/2) over all
+//   H*W keys; h = w v) — the [S,S] score matrix never reaches HBM here.
+// Input is the fused QKV projection [N][S][3C] bf16 (q | k | v per pixel), output [N][S][C] bf16 + logsumexp [N][S] fp32.
+//
+// Forward: one CTA owns 128 query rows (TMEM lanes) and walks the keys in tiles of 64.
+//   warp 0    TMA producer: Q once, then (K_j, V_j) into a 2-stage ring
+//   warp 1    MMA issuer : S_j = Q K_j^T (SS, fp32 in TMEM) ; O += P_j V_j (A = P_j from TMEM, B = V_j MN-major)
+//   warps 2-5 softmax    : thread == query row; S_j -> registers, running max with lazy rescale of O, exp2, P_j -> TMEM (bf16,
+//                          two buffers)
+// S_{j+1} is issued as soon as S_j has been read into registers, so the tensor pipe works under the exponentials.
+// Two CTAs fit one SM (256 TMEM columns and ~99 KB of shared memory each), which overlaps the rest.
+#include "hd_tc_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int BM = 128;                 // query rows per CTA
+constexpr int BN = 64;                  // keys per tile
+constexpr int D = 128;                  // head dim (= channels)
+constexpr int kQBytes = BM * D * 2;     // 32 KB: two [128 rows][64 ch] blocks
+constexpr int kKBytes = BN * D * 2;     // 16 KB: two [64 keys][64 ch] blocks
+constexpr int kStageBytes = 2 * kKBytes;
+constexpr int kStages = 2;
+constexpr uint32_t kColS = 0, kColP = 64, kColO = 128, kTmemCols = 256;
+constexpr float kRescaleThreshold = 8.f;   // log2 units: P <= 2^8 relative to the stale reference max
+
+struct AttnFwdParams {
+    int N, S, tiles;
+    float scale_log2;
+    __nv_bfloat16* out; float* lse;
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnFwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + kQBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kQBytes + kStages * kStageBytes);
+    uint64_t* q_full = bars;              // [1]
+    uint64_t* kv_full = bars + 1;         // [2]
+    uint64_t* kv_empty = bars + 3;        // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_empty = bars + 6;
+    uint64_t* p_full = bars + 7;
+    uint64_t* pv_done = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BM, n = blockIdx.y;
+    const int T = p.tiles;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapQKV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, kQBytes);
+            for (int blk = 0; blk < 2; ++blk)
+                for (int half = 0; half < 2; ++half)
+                    tma_load_3d(sQ + blk * (kQBytes / 2) + half * 8192, &mapQKV, q_full, blk * 64, q0 + half * 64, n);
+            for (int j = 0; j < T; ++j) {
+                const int s = j & 1;
+                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], kStageBytes);
+                uint8_t* st = sKV + s * kStageBytes;
+                for (int blk = 0; blk < 2; ++blk) tma_load_3d(st + blk * 8192, &mapQKV, &kv_full[s], D + blk * 64, j * BN, n);
+                for (int blk = 0; blk < 2; ++blk) tma_load_3d(st + kKBytes + blk * 8192, &mapQKV, &kv_full[s], 2 * D + blk * 64, j * BN, n);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);
+            const uint32_t idesc_pv = umma_idesc_bf16(BM, D, 0, 1);
+            const uint32_t aQ = smem_u32(sQ);
+            auto issue_s = [&](int j) {
+                const int s = j & 1;
+                mbar_wait(&kv_full[s], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t aK = smem_u32(sKV + s * kStageBytes);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {            // K = 16 channels per instruction
+                    const int blk = kk >> 2, sub = kk & 3;
+                    umma_bf16(tmem_base + kColS, umma_smem_desc(aQ + blk * (kQBytes / 2) + sub * 32, 16, 1024),
+                              umma_smem_desc(aK + blk * 8192 + sub * 32, 16, 1024), idesc_s, kk != 0);
+                }
+                umma_commit(s_full);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < T; ++j) {
+                if (j + 1 < T) {
+                    mbar_wait(s_empty, j & 1);               // S_j is in registers: the columns are free
+                    tc_fence_after();
+                    issue_s(j + 1);
+                }
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+                const int s = j & 1;
+                const uint32_t aV = smem_u32(sKV + s * kStageBytes + kKBytes);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)               // K = 16 keys per instruction = 2048 B of V rows
+                    umma_bf16_ts(tmem_base + kColO, tmem_base + kColP + (j & 1) * 32 + kk * 8, umma_smem_desc(aV + kk * 2048, 8192, 1024),
+                                 idesc_pv, (j | kk) != 0);
+                umma_commit(&kv_empty[s]);
+                umma_commit(pv_done);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const float sl2 = p.scale_log2;
+        float m_ref = 0.f, l = 0.f;
+        for (int j = 0; j < T; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t v[64];
+            tmem_ld32(lane_base + kColS, v);
+            tmem_ld32(lane_base + kColS + 32, v + 32);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);
+            float mx = __uint_as_float(v[0]);
+#pragma unroll
+            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            mx *= sl2;
+            if (j == 0) {
+                m_ref = mx;
+            } else {
+                const bool grow = mx > m_ref + kRescaleThreshold;
+                if (__any_sync(0xffffffffu, grow)) {
+                    float alpha = 1.f;
+                    if (grow) { alpha = fast_exp2(m_ref - mx); m_ref = mx; l *= alpha; }
+                    mbar_wait(pv_done, (j - 1) & 1);         // O must be at rest: P_{j-1} V_{j-1} has completed
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < D; c += 32) {
+                        uint32_t o[32];
+                        tmem_ld32(lane_base + kColO + c, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(lane_base + kColO + c, o);
+                    }
+                    tmem_wait_st();
+                }
+            }
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float a = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sl2, -m_ref));
+                const float b = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_ref));
+                l += a + b;
+                pk[i] = pack_bf16x2(a, b);
+            }
+            // P is double-buffered: P_j V_j may still be running when P_{j+1} is written; S_{j+2} (whose completion
+            // gates the next write to this buffer) is issued after P_j V_j, so no further wait is needed
+            tmem_st32(lane_base + kColP + (j & 1) * 32, pk);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(pv_done, (T - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.f / l;
+        __nv_bfloat16* orow = p.out + ((long long)n * p.S + q0 + row) * D;
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(lane_base + kColO + c, o);
+            tmem_wait_ld();
+            uint4* dst = reinterpret_cast<uint4*>(orow + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 w;
+                w.x = pack_bf16x2(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+                w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+                w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+                w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+                dst[i] = w;
+            }
+        }
+        p.lse[(long long)n * p.S + q0 + row] = (m_ref + log2f(l)) * 0.6931471805599453f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+int make_qkv_map(CUtensorMap* m, const void* qkv, int N, int S, int C3, int box_rows) {
+    uint64_t dims[3] = {(uint64_t)C3, (uint64_t)S, (uint64_t)N};
+    uint64_t str[2] = {(uint64_t)C3, (uint64_t)S * C3};
+    uint32_t box[3] = {64, (uint32_t)box_rows, 1};
+    return hd_make_tmap_bf16(m, qkv, 3, dims, str, box);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward.  Two launches of one templated kernel, no atomics, deterministic:
+//   kDQ = true : the CTA owns 128 QUERY rows (X0 = Q, X1 = dO) and walks key tiles (Y0 = K, Y1 = V):   dQ  += dS K
+//   kDQ = false: the CTA owns 128 KEY rows   (X0 = K, X1 = V ) and walks query tiles (Y0 = Q, Y1 = dO): dK += dS^T Q, dV += P^T dO
+// Per ring tile (64 rows of Y):
+//   St  = X0 Y0^T   (scores, or their transpose)          SS MMA, fp32 in TMEM
+//   dPt = X1 Y1^T   (dO V^T, or its transpose)            SS MMA
+//   threads (lane = row of X): P = exp2(St * scale*log2e - lse*log2e), dS = P * (dPt - delta)   -> bf16 in TMEM (two buffers)
+//   acc0 += dS Y0   [+ acc1 += P Y1]                      A from TMEM, B = the same Y tiles read MN-major
+// `stats` = [N][S][2] fp32 (lse*log2e, delta = rowsum(dO * O)), written by attn_stats_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBwdStages = 3;
+constexpr int kXBytes = BM * D * 2;        // 32 KB per stationary operand
+constexpr int kYBytes = BN * D * 2;        // 16 KB per ring operand
+constexpr int kBwdStageBytes = 2 * kYBytes;
+constexpr uint32_t kColSt = 0, kColdPt = 64, kColPd = 128 /* 2 x (dS 32 | P 32) */, kColAcc0 = 256, kColAcc1 = 384;
+
+struct AttnBwdParams {
+    int N, S, tiles;
+    float scale_log2, scale;
+    const float2* stats;
+    __nv_bfloat16* dqkv;
+};
+
+template <bool kDQ>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO, const AttnBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sX0 = smem;
+    uint8_t* sX1 = smem + kXBytes;
+    uint8_t* sY = smem + 2 * kXBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kXBytes + kBwdStages * kBwdStageBytes);
+    uint64_t* x_full = bars;                       // [1]
+    uint64_t* y_full = bars + 1;                   // [3]
+    uint64_t* y_empty = bars + 1 + kBwdStages;     // [3]
+    uint64_t* s_full = bars + 1 + 2 * kBwdStages;
+    uint64_t* s_empty = s_full + 1;
+    uint64_t* p_full = s_full + 2;
+    uint64_t* acc_done = s_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * BM, n = blockIdx.y;
+    const int T = p.tiles;
+    // channel offsets inside the qkv rows
+    constexpr int cX0 = kDQ ? 0 : D, cX1 = kDQ ? 0 : 2 * D, cY0 = kDQ ? D : 0, cY1 = kDQ ? 2 * D : 0;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapQKV); tma_prefetch_desc(&mapDO);
+        mbar_init(x_full, 1);
+        for (int s = 0; s < kBwdStages; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
+        mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(acc_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const CUtensorMap* mX1 = kDQ ? &mapDO : &mapQKV;
+            const CUtensorMap* mY1 = kDQ ? &mapQKV : &mapDO;
+            mbar_arrive_expect_tx(x_full, 2 * kXBytes);
+            for (int blk = 0; blk < 2; ++blk)
+                for (int half = 0; half < 2; ++half) {
+                    tma_load_3d(sX0 + blk * (kXBytes / 2) + half * 8192, &mapQKV, x_full, cX0 + blk * 64, r0 + half * 64, n);
+                    tma_load_3d(sX1 + blk * (kXBytes / 2) + half * 8192, mX1, x_full, cX1 + blk * 64, r0 + half * 64, n);
+                }
+            int stage = 0; uint32_t phase = 0;
+            for (int j = 0; j < T; ++j) {
+                mbar_wait(&y_empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&y_full[stage], kBwdStageBytes);
+                uint8_t* st = sY + stage * kBwdStageBytes;
+                for (int blk = 0; blk < 2; ++blk) tma_load_3d(st + blk * 8192, &mapQKV, &y_full[stage], cY0 + blk * 64, j * BN, n);
+                for (int blk = 0; blk < 2; ++blk) tma_load_3d(st + kYBytes + blk * 8192, mY1, &y_full[stage], cY1 + blk * 64, j * BN, n);
+                if (++stage == kBwdStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);
+            const uint32_t idesc_acc = umma_idesc_bf16(BM, D, 0, 1);
+            const uint32_t aX0 = smem_u32(sX0), aX1 = smem_u32(sX1);
+            int ld_stage = 0; uint32_t ld_phase = 0;
+            auto issue_s = [&]() {
+                mbar_wait(&y_full[ld_stage], ld_phase);
+                tc_fence_after();
+                const uint32_t aY0 = smem_u32(sY + ld_stage * kBwdStageBytes), aY1 = aY0 + kYBytes;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int blk = kk >> 2, sub = kk & 3;
+                    umma_bf16(tmem_base + kColSt, umma_smem_desc(aX0 + blk * (kXBytes / 2) + sub * 32, 16, 1024),
+                              umma_smem_desc(aY0 + blk * 8192 + sub * 32, 16, 1024), idesc_s, kk != 0);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int blk = kk >> 2, sub = kk & 3;
+                    umma_bf16(tmem_base + kColdPt, umma_smem_desc(aX1 + blk * (kXBytes / 2) + sub * 32, 16, 1024),
+                              umma_smem_desc(aY1 + blk * 8192 + sub * 32, 16, 1024), idesc_s, kk != 0);
+                }
+                umma_commit(s_full);
+                if (++ld_stage == kBwdStages) { ld_stage = 0; ld_phase ^= 1; }
+            };
+            mbar_wait(x_full, 0);
+            issue_s();
+            int stage = 0;
+            for (int j = 0; j < T; ++j) {
+                if (j + 1 < T) {
+                    mbar_wait(s_empty, j & 1);
+                    tc_fence_after();
+                    issue_s();
+                }
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+                const uint32_t aY0 = smem_u32(sY + stage * kBwdStageBytes), aY1 = aY0 + kYBytes;
+                const uint32_t tPd = tmem_base + kColPd + (j & 1) * 64;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16_ts(tmem_base + kColAcc0, tPd + kk * 8, umma_smem_desc(aY0 + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0);
+                if (!kDQ) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16_ts(tmem_base + kColAcc1, tPd + 32 + kk * 8, umma_smem_desc(aY1 + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0);
+                }
+                umma_commit(&y_empty[stage]);
+                if (++stage == kBwdStages) stage = 0;
+            }
+            umma_commit(acc_done);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const float sl2 = p.scale_log2;
+        const float2* stats_n = p.stats + (long long)n * p.S;
+        float2 my = make_float2(0.f, 0.f);
+        if (kDQ) my = __ldg(stats_n + r0 + row);
+        for (int j = 0; j < T; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            const uint32_t tPd = lane_base + kColPd + (j & 1) * 64;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t sv[32], dv[32];
+                tmem_ld32(lane_base + kColSt + h * 32, sv);
+                tmem_ld32(lane_base + kColdPt + h * 32, dv);
+                tmem_wait_ld();
+                if (h == 1) {                      // both halves are in registers: the score columns are free
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_empty);
+                }
+                uint32_t pp[16], ds[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float2 s0 = my, s1 = my;
+                    if (!kDQ) {
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(stats_n + j * BN + h * 32 + 2 * i));
+                        s0 = make_float2(q.x, q.y); s1 = make_float2(q.z, q.w);
+                    }
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * i]), sl2, -s0.x));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -s1.x));
+                    const float d0 = p0 * (__uint_as_float(dv[2 * i]) - s0.y);
+                    const float d1 = p1 * (__uint_as_float(dv[2 * i + 1]) - s1.y);
+                    pp[i] = pack_bf16x2(p0, p1);
+                    ds[i] = pack_bf16x2(d0, d1);
+                }
+                tmem_st16(tPd + h * 16, ds);
+                if (!kDQ) tmem_st16(tPd + 32 + h * 16, pp);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(acc_done, 0);
+        tc_fence_after();
+        __nv_bfloat16* orow = p.dqkv + ((long long)n * p.S + r0 + row) * (3 * D) + (kDQ ? 0 : D);
+#pragma unroll 1
+        for (int a = 0; a < (kDQ ? 1 : 2); ++a) {
+            const float mul = a == 0 ? p.scale : 1.f;
+#pragma unroll 1
+            for (int c = 0; c < D; c += 32) {
+                uint32_t o[32];
+                tmem_ld32(lane_base + (a == 0 ? kColAcc0 : kColAcc1) + c, o);
+                tmem_wait_ld();
+                uint4* dst = reinterpret_cast<uint4*>(orow + a * D + c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 w;
+                    w.x = pack_bf16x2(__uint_as_float(o[8 * i]) * mul, __uint_as_float(o[8 * i + 1]) * mul);
+                    w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * mul, __uint_as_float(o[8 * i + 3]) * mul);
+                    w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * mul, __uint_as_float(o[8 * i + 5]) * mul);
+                    w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * mul, __uint_as_float(o[8 * i + 7]) * mul);
+                    dst[i] = w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// stats[row] = (lse * log2e, sum_c dO * O); one warp per row of C = 128 channels
+__global__ void attn_stats_kernel(const __nv_bfloat16* o, const __nv_bfloat16* dout, const float* lse, float2* stats, long long rows) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(o + r * D) + lane);
+    const uint2 b = __ldg(reinterpret_cast<const uint2*>(dout + r * D) + lane);
+    const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&b);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float2 x = __bfloat1622float2(ah[i]), y = __bfloat1622float2(bh[i]);
+        acc += x.x * y.x + x.y * y.y;
+    }
+    acc = hd_warp_sum(acc);
+    if (lane == 0) stats[r] = make_float2(lse[r] * 1.4426950408889634f, acc);
+}
+
+}  // namespace
+
+extern "C" int hd_attn_tc_supported(int S, int C) { return (C == D && S >= BM && S % BM == 0) ? 1 : 0; }
+extern "C" int hd_attn_bwd_tc_supported(int S, int C) { return hd_attn_tc_supported(S, C); }
+
+extern "C" int hd_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int S, int C, cudaStream_t stream) {
+    HD_REQUIRE(qkv && out && lse && N > 0);
+    if (!hd_attn_tc_supported(S, C)) { hd_set_error("hd_attn_fwd_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
+    CUtensorMap m;
+    int rc = make_qkv_map(&m, qkv, N, S, 3 * C, 64); if (rc) return rc;
+    AttnFwdParams p{};
+    p.N = N; p.S = S; p.tiles = S / BN;
+    p.scale_log2 = 1.4426950408889634f / sqrtf((float)C);
+    p.out = (__nv_bfloat16*)out; p.lse = lse;
+    const size_t smem = kQBytes + kStages * kStageBytes + 1024 + 16 * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(attn_fwd_tc_kernel)"); return HD_ERR_CUDA; }
+        attr_set = true;
+    }
+    attn_fwd_tc_kernel<<<dim3(S / BM, N), kThreads, smem, stream>>>(m, p);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+
+// stats: scratch of N*S*2 floats ((lse*log2e, delta) per row)
+extern "C" int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* stats, void* dqkv,
+                              int N, int S, int C, cudaStream_t stream) {
+    HD_REQUIRE(qkv && out && dout && lse && stats && dqkv && N > 0);
+    if (!hd_attn_bwd_tc_supported(S, C)) { hd_set_error("hd_attn_bwd_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
+    CUtensorMap mQKV, mDO;
+    int rc = make_qkv_map(&mQKV, qkv, N, S, 3 * C, 64); if (rc) return rc;
+    rc = make_qkv_map(&mDO, dout, N, S, C, 64); if (rc) return rc;
+    const long long rows = (long long)N * S;
+    attn_stats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse, (float2*)stats, rows);
+    HD_CHECK_LAUNCH();
+    AttnBwdParams p{};
+    p.N = N; p.S = S; p.tiles = S / BN;
+    p.scale = 1.f / sqrtf((float)C);
+    p.scale_log2 = 1.4426950408889634f * p.scale;
+    p.stats = (const float2*)stats; p.dqkv = (__nv_bfloat16*)dqkv;
+    const size_t smem = 2 * kXBytes + kBwdStages * kBwdStageBytes + 1024 + 16 * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            hd_set_error("cudaFuncSetAttribute(attn_bwd_tc_kernel)"); return HD_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    attn_bwd_tc_kernel<false><<<dim3(S / BM, N), kThreads, smem, stream>>>(mQKV, mDO, p);
+    HD_CHECK_LAUNCH();
+    attn_bwd_tc_kernel<true><<<dim3(S / BM, N), kThreads, smem, stream>>>(mQKV, mDO, p);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}

@@ -187,9 +187,11 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams 
                                                             double* gsums, float* dgamma, float* dbeta) {
     constexpr int V = Vec<T>::N;
     __shared__ float s_mean[64], s_rstd[64], sg[64][2];
+    extern __shared__ float s_ch[];               // [2][C]: per-channel (dgamma, dbeta) partials of this block
     const int n = blockIdx.y;
     gn_load_stats(g, n, s_mean, s_rstd);
     for (int i = threadIdx.x; i < g.G; i += blockDim.x) { sg[i][0] = 0.f; sg[i][1] = 0.f; }
+    for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) s_ch[i] = 0.f;
     __syncthreads();
     const int lanes = g.C / V, cpg = g.C / g.G;
     const int ppi = blockDim.x / lanes;
@@ -219,11 +221,12 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams 
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             int c = c0 + k, gi = c / cpg;
-            atomicAdd(dgamma + c, s2[k]); atomicAdd(dbeta + c, s1[k]);
+            atomicAdd(&s_ch[c], s2[k]); atomicAdd(&s_ch[g.C + c], s1[k]);     // block-level first: one global atomic per channel per block
             atomicAdd(&sg[gi][0], gam[k] * s1[k]); atomicAdd(&sg[gi][1], gam[k] * s2[k]);
         }
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < g.C; i += blockDim.x) { atomicAdd(dgamma + i, s_ch[i]); atomicAdd(dbeta + i, s_ch[g.C + i]); }
     for (int i = threadIdx.x; i < g.G; i += blockDim.x) {
         atomicAdd(gsums + ((int64_t)n * g.G + i) * 2, (double)sg[i][0]);
         atomicAdd(gsums + ((int64_t)n * g.G + i) * 2 + 1, (double)sg[i][1]);
@@ -236,7 +239,7 @@ static int gn_bwd_reduce_t(const void* in0, int C0, const void* in1, int C1, GnP
     if (cudaMemsetAsync(gsums, 0, sizeof(double) * 2 * (size_t)g.N * g.G, st) != cudaSuccess) return HD_ERR_CUDA;
     int ppi = 256 / (g.C / Vec<T>::N), chunks;
     int64_t ppb = pick_chunk(g.N, g.HW, ppi, &chunks);
-    gn_bwd_reduce_kernel<T><<<dim3(chunks, g.N), 256, 0, st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (const T*)dy, ppb, gsums, dgamma, dbeta);
+    gn_bwd_reduce_kernel<T><<<dim3(chunks, g.N), 256, 2 * g.C * sizeof(float), st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (const T*)dy, ppb, gsums, dgamma, dbeta);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }
@@ -333,21 +336,27 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* t, int N, int64_t 
     constexpr int V = Vec<T>::N;
     const int lanes = C / V, ppi = blockDim.x / lanes;
     const int lane = threadIdx.x % lanes, sub = threadIdx.x / lanes, n = blockIdx.y;
-    if (sub >= ppi) return;
-    float s[V];
+    extern __shared__ float s_col[];              // [C] partial of this block: one global atomic per channel per block
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_col[i] = 0.f;
+    __syncthreads();
+    if (sub < ppi) {
+        float s[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) s[k] = 0.f;
-    const int64_t p0 = blockIdx.x * pix_per_block;
-    const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
-    for (int64_t p = p0 + sub; p < p1; p += ppi) {
-        float v[V]; vec_load(t + ((int64_t)n * HW + p) * C + lane * V, v);
+        for (int k = 0; k < V; ++k) s[k] = 0.f;
+        const int64_t p0 = blockIdx.x * pix_per_block;
+        const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
+        for (int64_t p = p0 + sub; p < p1; p += ppi) {
+            float v[V]; vec_load(t + ((int64_t)n * HW + p) * C + lane * V, v);
 #pragma unroll
-        for (int k = 0; k < V; ++k) s[k] += v[k];
+            for (int k = 0; k < V; ++k) s[k] += v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) atomicAdd(&s_col[lane * V + k], s[k]);
     }
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-        if (per_n) atomicAdd(per_n + (int64_t)n * ld + lane * V + k, s[k]);
-        if (total) atomicAdd(total + lane * V + k, s[k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        if (per_n) atomicAdd(per_n + (int64_t)n * ld + i, s_col[i]);
+        if (total) atomicAdd(total + i, s_col[i]);
     }
 }
 __global__ void colsum_nchw_kernel(const float* t, int C, int64_t HW, float* per_n, int64_t ld, float* total) {
@@ -379,8 +388,8 @@ extern "C" int hd_colsum(int dtype, const void* t, int nchw_f32, int N, int64_t 
     if (C % V != 0 || C / V > 256) { hd_set_error("colsum: unsupported channel count"); return HD_ERR_UNSUPPORTED; }
     int ppi = 256 / (C / V), chunks;
     int64_t ppb = pick_chunk(N, HW, ppi, &chunks);
-    if (dtype == HD_F32) colsum_kernel<float><<<dim3(chunks, N), 256, 0, stream>>>((const float*)t, N, HW, C, ppb, per_n, ld_per_n, total);
-    else if (dtype == HD_BF16) colsum_kernel<__nv_bfloat16><<<dim3(chunks, N), 256, 0, stream>>>((const __nv_bfloat16*)t, N, HW, C, ppb, per_n, ld_per_n, total);
+    if (dtype == HD_F32) colsum_kernel<float><<<dim3(chunks, N), 256, C * sizeof(float), stream>>>((const float*)t, N, HW, C, ppb, per_n, ld_per_n, total);
+    else if (dtype == HD_BF16) colsum_kernel<__nv_bfloat16><<<dim3(chunks, N), 256, C * sizeof(float), stream>>>((const __nv_bfloat16*)t, N, HW, C, ppb, per_n, ld_per_n, total);
     else return HD_ERR_ARG;
     HD_CHECK_LAUNCH();
     return HD_OK;

@@ -123,9 +123,10 @@ class CudaOps:
 
     def attn_bwd(self, qkv, out, dout, lse, delta, dqkv, N, S, C):
         e0 = self._t0()
-        tc = self.use_tc and qkv.dtype == torch.bfloat16 and self.lib.hd_attn_tc_supported(S, C)
-        if self.use_tc and qkv.dtype == torch.bfloat16 and self.lib.hd_attn_tc_supported(S, C):
-            _lib.check(self.lib.hd_attn_bwd_tc(_p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), N, S, C, _stream()), "hd_attn_bwd_tc")
+        tc = self.use_tc and qkv.dtype == torch.bfloat16 and self.lib.hd_attn_bwd_tc_supported(S, C)
+        if tc:
+            stats = torch.empty((N, S, 2), dtype=torch.float32, device=qkv.device)   # (lse*log2e, rowsum(dO*O)) scratch
+            _lib.check(self.lib.hd_attn_bwd_tc(_p(qkv), _p(out), _p(dout), _p(lse), _p(stats), _p(dqkv), N, S, C, _stream()), "hd_attn_bwd_tc")
             self.tc_launches += 2
         else:
             _lib.check(self.lib.hd_attn_bwd_simt(_DT[qkv.dtype], _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), N, S, C, _stream()), "hd_attn_bwd_simt")

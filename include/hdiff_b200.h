@@ -56,9 +56,12 @@ int hd_wgrad_tc(const void* in0, int C0, const void* in1, int C1, int P_in, cons
 int hd_attn_fwd_simt(int dtype, const void* qkv, void* out, float* lse, int N, int S, int C, hd_stream_t stream);
 int hd_attn_bwd_simt(int dtype, const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
                      void* dqkv, int N, int S, int C, hd_stream_t stream);
-int hd_attn_tc_supported(int S, int C);
+int hd_attn_tc_supported(int S, int C);      /* forward on tcgen05 */
+int hd_attn_bwd_tc_supported(int S, int C);  /* backward on tcgen05 */
 int hd_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int S, int C, hd_stream_t stream);
-int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+/* tcgen05 flash attention (K5).  Backward = three launches (row statistics, dK/dV pass, dQ pass), deterministic, no
+ * atomics; `stats` is caller-provided scratch of N*S*2 floats ((lse*log2e, rowsum(dout*out)) per row). */
+int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* stats, void* dqkv,
                    int N, int S, int C, hd_stream_t stream);
 
 /* ---- GroupNorm(32) + Swish (+ Dropout): ModelCondition.py:128-129,141-143,95,249-250.  Two-source input

@@ -218,6 +218,59 @@ def test_attention_forward_backward(dtype, tol, S, C):
     assert _rel(dqkv.float(), rd) < tol, _rel(dqkv.float(), rd)
 
 
+@pytest.mark.parametrize("S,N,qscale", [(128, 2, 1.0), (256, 3, 1.0), (1024, 2, 1.0), (4096, 1, 1.0), (1024, 2, 6.0), (2048, 1, 12.0)])
+def test_attention_tcgen05_forward(S, N, qscale):
+    """Flash-style tcgen05 forward against softmax(q k^T C^-1/2) v in fp32; `qscale` sharpens the scores so that the
+    running maximum moves by more than the lazy-rescale threshold (the O-rescale path runs)."""
+    dev = torch.device("cuda")
+    ops, emu = _ops(), EmuOps()
+    C = 128
+    assert ops.lib.hd_attn_tc_supported(S, C)
+    torch.manual_seed(S + int(qscale))
+    qkv = torch.randn(N, S, 3 * C, device=dev)
+    qkv[:, :, :C] *= qscale
+    # ascending key norms along the sequence make later tiles raise the maximum
+    qkv[:, :, C:2 * C] *= torch.linspace(0.5, 1.5, S, device=dev)[None, :, None]
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.empty(N, S, C, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(N, S, device=dev)
+    before = ops.tc_launches
+    ops.attn_fwd(qkv, out, lse, N, S, C)
+    torch.cuda.synchronize()
+    assert ops.tc_launches == before + 1
+    ro, rl = torch.empty(N, S, C, device=dev), torch.empty(N, S, device=dev)
+    emu.attn_fwd(qkv.float(), ro, rl, N, S, C)
+    assert _rel(out.float(), ro) < 1e-2, _rel(out.float(), ro)           # bf16 tolerance (north_star)
+    assert float((lse - rl).abs().max()) < 2e-2 * max(1.0, float(rl.abs().max()) * 0.05), float((lse - rl).abs().max())
+
+
+@pytest.mark.parametrize("S,N,qscale", [(128, 2, 1.0), (256, 3, 1.0), (1024, 2, 1.0), (4096, 1, 1.0), (1024, 2, 4.0)])
+def test_attention_tcgen05_backward(S, N, qscale):
+    """dQ / dK / dV of the tcgen05 backward (two deterministic passes, no atomics) against autograd of the fp32 formula."""
+    dev = torch.device("cuda")
+    ops, emu = _ops(), EmuOps()
+    C = 128
+    assert ops.lib.hd_attn_bwd_tc_supported(S, C)
+    torch.manual_seed(7 * S + int(qscale))
+    qkv = torch.randn(N, S, 3 * C, device=dev)
+    qkv[:, :, :C] *= qscale
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.empty(N, S, C, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(N, S, device=dev)
+    ops.attn_fwd(qkv, out, lse, N, S, C)
+    dout = torch.randn(N, S, C, device=dev).to(torch.bfloat16)
+    dqkv = torch.full_like(qkv, float("nan"))
+    before = ops.tc_launches
+    ops.attn_bwd(qkv, out, dout, lse, None, dqkv, N, S, C)
+    torch.cuda.synchronize()
+    assert ops.tc_launches == before + 2
+    rd = torch.empty(N, S, 3 * C, device=dev)
+    emu.attn_bwd(qkv.float(), None, dout.float(), None, None, rd, N, S, C)
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        r = _rel(dqkv[:, :, sl].float(), rd[:, :, sl])
+        assert r < 1.5e-2, (name, r)
+
+
 def test_embedding_path_and_packing_kernels():
     dev = torch.device("cuda")
     ops, emu = _ops(), EmuOps()

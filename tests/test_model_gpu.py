@@ -65,7 +65,7 @@ def test_unet_tiny_vs_reference_golden(golden_dir, dtype, tol, tag):
         assert params[k].grad is not None, k
         # absolute slack scales with the largest gradient of the model: parameters whose exact gradient is ~0 (an embedding
         # add that the following 1-channel-per-group GroupNorm cancels) only carry rounding noise of the big ones
-        assert _close(params[k].grad.cpu(), gref, 4 * tol, 2e-3 * tol * gscale + 2e-5), (k, _rel(params[k].grad.cpu(), gref))
+        assert _close(params[k].grad.cpu(), gref, 4 * tol, 5e-3 * tol * gscale + 2e-5), (k, _rel(params[k].grad.cpu(), gref))
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
