@@ -51,21 +51,29 @@ __device__ __forceinline__ float hd_sigmoid(float x) { return 1.f / (1.f + __exp
 __device__ __forceinline__ float hd_swish(float x) { return x * hd_sigmoid(x); }
 __device__ __forceinline__ float hd_swish_grad(float x) { float s = hd_sigmoid(x); return s * (1.f + x * (1.f - s)); }
 
-// Counter-based RNG for dropout: one 32-bit draw per (seed, element index); the backward pass
-// regenerates the mask from the same (seed, index) instead of storing it.
-__host__ __device__ __forceinline__ uint32_t hd_hash_u32(uint64_t seed, uint64_t idx) {
-    uint64_t z = idx * 0x9E3779B97F4A7C15ull + seed;
-    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
-    z ^= z >> 27; z *= 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (uint32_t)(z >> 32);
+// Counter-based RNG for dropout: one 32-bit hash per PAIR of consecutive elements, 16 uniform bits per element
+// (drop probability resolution 2^-16); the backward pass regenerates the mask from the same (seed, index) instead
+// of storing it.  ~3 integer instructions per element, so the GroupNorm kernels stay HBM-bound with dropout on.
+__host__ __device__ __forceinline__ uint32_t hd_hash_pair(uint64_t seed, uint64_t pair) {
+    uint32_t h = (uint32_t)pair * 0x9E3779B1u + (uint32_t)seed;
+    h ^= ((uint32_t)(pair >> 32) + (uint32_t)(seed >> 32)) * 0x85EBCA77u;
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
 }
-__host__ __device__ __forceinline__ float hd_dropout_scale(uint64_t seed, uint64_t idx, float p_drop) {
-    // returns 0 (dropped) or 1/(1-p)
-    if (p_drop <= 0.f) return 1.f;
-    uint32_t r = hd_hash_u32(seed, idx);
-    float u = (float)(r >> 8) * (1.f / 16777216.f);
-    return u < p_drop ? 0.f : 1.f / (1.f - p_drop);
+__host__ __device__ __forceinline__ uint32_t hd_dropout_threshold(float p_drop) { return (uint32_t)(p_drop * 65536.f + 0.5f); }
+// scale[k] = 0 (dropped) or 1/(1-p) for the V consecutive elements starting at the EVEN element index `base`
+template <int V>
+__host__ __device__ __forceinline__ void hd_dropout_vec(uint64_t seed, uint64_t base, float p_drop, float* scale) {
+    const uint32_t thr = hd_dropout_threshold(p_drop);
+    const float keep = 1.f / (1.f - p_drop);
+#pragma unroll
+    for (int k = 0; k < V; k += 2) {
+        const uint32_t h = hd_hash_pair(seed, (base >> 1) + (k >> 1));
+        scale[k] = (h & 0xFFFFu) < thr ? 0.f : keep;
+        scale[k + 1] = (h >> 16) < thr ? 0.f : keep;
+    }
 }
 
 __device__ __forceinline__ float hd_warp_sum(float v) {

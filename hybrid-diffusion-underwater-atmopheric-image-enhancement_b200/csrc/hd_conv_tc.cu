@@ -26,6 +26,7 @@ struct ConvTcParams {
     int Cout, P_out;
     const float* bias; const float* emb; long long emb_stride;
     const __nv_bfloat16* res; __nv_bfloat16* out;
+    float* out_nchw; int nchw_c;     // tail: store only the first nchw_c (<= 16) channels, fp32 NCHW
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -118,6 +119,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
             const float* emb_row = p.emb ? p.emb + (long long)n * p.emb_stride : nullptr;
+            if (p.out_nchw) {
+                if (n_tile == 0) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr, v);
+                    tmem_wait_ld();
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (i < p.nchw_c) {
+                                float f = __uint_as_float(v[i]);
+                                if (p.bias) f += __ldg(p.bias + i);
+                                p.out_nchw[(((long long)n * p.nchw_c + i) * p.H + y) * p.W + x] = f;
+                            }
+                        }
+                    }
+                }
+            } else
             for (int c = 0; c < p.NT; c += 16) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c, v);
@@ -243,8 +261,9 @@ extern "C" int hd_conv_tc_supported(int C0, int C1, int P_in, int Cout, int P_ou
 
 extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int P_in, const void* w, const float* bias,
                           const float* emb, int64_t emb_stride, const void* res, void* out, int Cout, int P_out,
-                          int N, int H, int W, int ksize, cudaStream_t stream) {
+                          int N, int H, int W, int ksize, int out_nchw_c, cudaStream_t stream) {
     HD_REQUIRE(in0 && w && out && N > 0);
+    HD_REQUIRE(out_nchw_c >= 0 && out_nchw_c <= 16 && (out_nchw_c == 0 || (P_out == 1 && !emb && !res)));
     if (!hd_conv_tc_supported(C0, C1, P_in, Cout, P_out, H, W, ksize)) { hd_set_error("hd_conv_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
     HD_REQUIRE(P_out == 1 || !emb);
     ConvTcParams p{};
@@ -264,6 +283,7 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     p.Cout = Cout; p.P_out = P_out;
     p.bias = bias; p.emb = emb; p.emb_stride = emb_stride;
     p.res = (const __nv_bfloat16*)res; p.out = (__nv_bfloat16*)out;
+    p.out_nchw = out_nchw_c ? (float*)out : nullptr; p.nchw_c = out_nchw_c;
 
     CUtensorMap mA0, mA1, mB;
     int rc = hd_make_act_tmap(&mA0, in0, C0, P_in, N, H, W, 64, p.TW, p.TH); if (rc) return rc;

@@ -132,26 +132,40 @@ extern "C" int hd_gn_stats(int dtype, const void* in0, int C0, const void* in1, 
 }
 
 // ------------------------------- apply (forward) --------------------------------------------
-// out[n][pix][c] = drop( act( (x - mean) * rstd * gamma + beta ) ); grid (chunks, N)
+// out[n][pix][c] = drop( act( (x - mean) * rstd * gamma + beta ) ); grid (chunks, N).
+// thread <-> fixed channel vector (scale / shift hoisted out of the pixel loop: one FMA per element before the activation)
 template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> x, GnParams g, T* out) {
+__global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> x, GnParams g, int64_t pix_per_block, T* out) {
     constexpr int V = Vec<T>::N;
     __shared__ float s_mean[64], s_rstd[64];
     const int n = blockIdx.y;
     gn_load_stats(g, n, s_mean, s_rstd);
     __syncthreads();
     const int lanes = g.C / V, cpg = g.C / g.G;
-    const int64_t nvec = g.HW * lanes;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = i / lanes; const int c0 = (int)(i - pix * lanes) * V;
+    const int ppi = blockDim.x / lanes;
+    const int lane = threadIdx.x % lanes, sub = threadIdx.x / lanes;
+    if (sub >= ppi) return;
+    const int c0 = lane * V;
+    float a[V], b[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int c = c0 + k, gi = c / cpg;
+        a[k] = s_rstd[gi] * g.gamma[c];
+        b[k] = g.beta[c] - s_mean[gi] * a[k];
+    }
+    const int64_t p0 = blockIdx.x * pix_per_block;
+    const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
+    const bool drop = g.p_drop > 0.f;
+    for (int64_t pix = p0 + sub; pix < p1; pix += ppi) {
         float v[V]; vec_load(x.at(n, pix, g.HW, c0), v);
         const int64_t obase = ((int64_t)n * g.HW + pix) * g.C + c0;
+        float ds[V];
+        if (drop) hd_dropout_vec<V>(g.seed, (uint64_t)obase, g.p_drop, ds);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            int c = c0 + k, gi = c / cpg;
-            float z = (v[k] - s_mean[gi]) * s_rstd[gi] * __ldg(g.gamma + c) + __ldg(g.beta + c);
+            float z = fmaf(v[k], a[k], b[k]);
             if (g.act) z = hd_swish(z);
-            if (g.p_drop > 0.f) z *= hd_dropout_scale(g.seed, (uint64_t)(obase + k), g.p_drop);
+            if (drop) z *= ds[k];
             v[k] = z;
         }
         vec_store(out + obase, v);
@@ -160,12 +174,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> x, GnParams g, T*
 template <typename T>
 static int gn_apply_t(const void* in0, int C0, const void* in1, int C1, GnParams g, void* out, cudaStream_t st) {
     int rc = gn_check<T>(C0, C1, g.G); if (rc) return rc;
-    int64_t nvec = g.HW * (g.C / Vec<T>::N);
-    int64_t chunks = (nvec + 1023) / 1024;
-    int64_t cap = ((int64_t)hd_num_sms() * 16 + g.N - 1) / g.N;
-    if (chunks > cap) chunks = cap;
-    if (chunks < 1) chunks = 1;
-    gn_apply_kernel<T><<<dim3((unsigned)chunks, g.N), 256, 0, st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (T*)out);
+    int ppi = 256 / (g.C / Vec<T>::N), chunks;
+    int64_t ppb = pick_chunk(g.N, g.HW, ppi, &chunks);
+    gn_apply_kernel<T><<<dim3((unsigned)chunks, g.N), 256, 0, st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, ppb, (T*)out);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }
@@ -208,12 +219,14 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams 
             vec_load(x.at(n, p, g.HW, c0), v);
             const int64_t obase = ((int64_t)n * g.HW + p) * g.C + c0;
             vec_load(dy + obase, d);
+            float ds[V];
+            if (g.p_drop > 0.f) hd_dropout_vec<V>(g.seed, (uint64_t)obase, g.p_drop, ds);
 #pragma unroll
             for (int k = 0; k < V; ++k) {
                 int gi = (c0 + k) / cpg;
                 float xh = (v[k] - s_mean[gi]) * s_rstd[gi];
                 float dd = d[k];
-                if (g.p_drop > 0.f) dd *= hd_dropout_scale(g.seed, (uint64_t)(obase + k), g.p_drop);
+                if (g.p_drop > 0.f) dd *= ds[k];
                 if (g.act) dd *= hd_swish_grad(xh * gam[k] + bet[k]);
                 s1[k] += dd; s2[k] += dd * xh;
             }
@@ -255,9 +268,10 @@ extern "C" int hd_gn_bwd_reduce(int dtype, const void* in0, int C0, const void* 
 
 // ------------------------------- backward, apply pass ---------------------------------------
 // dx = rstd * (gamma dy' - A/m - xhat B/m) + add + acc ; written to two destination tensors.
+// thread <-> fixed channel vector, per-channel constants hoisted out of the pixel loop.
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g, const T* dy, const double* gsums, const T* add,
-                                                           const T* acc0, const T* acc1, T* dx0, T* dx1) {
+                                                           const T* acc0, const T* acc1, T* dx0, T* dx1, int64_t pix_per_block) {
     constexpr int V = Vec<T>::N;
     __shared__ float s_mean[64], s_rstd[64], s_a[64], s_b[64];
     const int n = blockIdx.y;
@@ -269,52 +283,58 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g
     }
     __syncthreads();
     const int lanes = g.C / V, cpg = g.C / g.G;
-    const int64_t nvec = g.HW * lanes;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = i / lanes; const int c0 = (int)(i - pix * lanes) * V;
+    const int ppi = blockDim.x / lanes;
+    const int lane = threadIdx.x % lanes, sub = threadIdx.x / lanes;
+    if (sub >= ppi) return;
+    const int c0 = lane * V;
+    float gam[V], bet[V], rs[V], mr[V], ca[V], cb[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int c = c0 + k, gi = c / cpg;
+        gam[k] = g.gamma[c]; bet[k] = g.beta[c];
+        rs[k] = s_rstd[gi]; mr[k] = -s_mean[gi] * s_rstd[gi];
+        ca[k] = s_rstd[gi] * s_a[gi]; cb[k] = s_rstd[gi] * s_b[gi];
+    }
+    const bool first = c0 < x.C0;
+    const int Cd = first ? x.C0 : x.C1, cd = first ? c0 : c0 - x.C0;
+    const T* acc = first ? acc0 : acc1;
+    T* dx = first ? dx0 : dx1;
+    const int64_t p0 = blockIdx.x * pix_per_block;
+    const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
+    const bool drop = g.p_drop > 0.f;
+    for (int64_t pix = p0 + sub; pix < p1; pix += ppi) {
         float v[V], d[V], r[V];
         vec_load(x.at(n, pix, g.HW, c0), v);
         const int64_t obase = ((int64_t)n * g.HW + pix) * g.C + c0;
         vec_load(dy + obase, d);
+        float ds[V];
+        if (drop) hd_dropout_vec<V>(g.seed, (uint64_t)obase, g.p_drop, ds);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            int c = c0 + k, gi = c / cpg;
-            float gam = __ldg(g.gamma + c);
-            float xh = (v[k] - s_mean[gi]) * s_rstd[gi];
+            const float xh = fmaf(v[k], rs[k], mr[k]);
             float dd = d[k];
-            if (g.p_drop > 0.f) dd *= hd_dropout_scale(g.seed, (uint64_t)(obase + k), g.p_drop);
-            if (g.act) dd *= hd_swish_grad(xh * gam + __ldg(g.beta + c));
-            r[k] = s_rstd[gi] * (gam * dd - s_a[gi] - xh * s_b[gi]);
+            if (drop) dd *= ds[k];
+            if (g.act) dd *= hd_swish_grad(fmaf(xh, gam[k], bet[k]));
+            r[k] = rs[k] * gam[k] * dd - ca[k] - xh * cb[k];
         }
-        if (add) { float a[V]; vec_load(add + obase, a);
+        if (add) { float t[V]; vec_load(add + obase, t);
 #pragma unroll
-            for (int k = 0; k < V; ++k) r[k] += a[k]; }
-        if (c0 < x.C0) {
-            const int64_t o = ((int64_t)n * g.HW + pix) * x.C0 + c0;
-            if (acc0) { float a[V]; vec_load(acc0 + o, a);
+            for (int k = 0; k < V; ++k) r[k] += t[k]; }
+        const int64_t o = ((int64_t)n * g.HW + pix) * Cd + cd;
+        if (acc) { float t[V]; vec_load(acc + o, t);
 #pragma unroll
-                for (int k = 0; k < V; ++k) r[k] += a[k]; }
-            vec_store(dx0 + o, r);
-        } else {
-            const int64_t o = ((int64_t)n * g.HW + pix) * x.C1 + (c0 - x.C0);
-            if (acc1) { float a[V]; vec_load(acc1 + o, a);
-#pragma unroll
-                for (int k = 0; k < V; ++k) r[k] += a[k]; }
-            vec_store(dx1 + o, r);
-        }
+            for (int k = 0; k < V; ++k) r[k] += t[k]; }
+        vec_store(dx + o, r);
     }
 }
 template <typename T>
 static int gn_bwd_apply_t(const void* in0, int C0, const void* in1, int C1, GnParams g, const void* dy, const double* gsums,
                           const void* add, const void* acc0, const void* acc1, void* dx0, void* dx1, cudaStream_t st) {
     int rc = gn_check<T>(C0, C1, g.G); if (rc) return rc;
-    int64_t nvec = g.HW * (g.C / Vec<T>::N);
-    int64_t chunks = (nvec + 1023) / 1024;
-    int64_t cap = ((int64_t)hd_num_sms() * 16 + g.N - 1) / g.N;
-    if (chunks > cap) chunks = cap;
-    if (chunks < 1) chunks = 1;
+    int ppi = 256 / (g.C / Vec<T>::N), chunks;
+    int64_t ppb = pick_chunk(g.N, g.HW, ppi, &chunks);
     gn_bwd_apply_kernel<T><<<dim3((unsigned)chunks, g.N), 256, 0, st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (const T*)dy, gsums,
-                                                                  (const T*)add, (const T*)acc0, (const T*)acc1, (T*)dx0, (T*)dx1);
+                                                                  (const T*)add, (const T*)acc0, (const T*)acc1, (T*)dx0, (T*)dx1, ppb);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }
@@ -391,6 +411,35 @@ extern "C" int hd_colsum(int dtype, const void* t, int nchw_f32, int N, int64_t 
     if (dtype == HD_F32) colsum_kernel<float><<<dim3(chunks, N), 256, C * sizeof(float), stream>>>((const float*)t, N, HW, C, ppb, per_n, ld_per_n, total);
     else if (dtype == HD_BF16) colsum_kernel<__nv_bfloat16><<<dim3(chunks, N), 256, C * sizeof(float), stream>>>((const __nv_bfloat16*)t, N, HW, C, ppb, per_n, ld_per_n, total);
     else return HD_ERR_ARG;
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+
+// ------------------------------- NCHW fp32 -> NHWC bf16, channel-padded ----------------------
+// The 3-channel network input (and the gradient of the 3-channel output) enter the tcgen05 convolution as a
+// 64-channel NHWC tensor whose channels >= Cin are zero (reference: head / tail nn.Conv2d, ModelCondition.py:219,251).
+// thread <-> pixel: coalesced plane reads, 128 contiguous bytes written per thread.
+__global__ void pad_nchw_kernel(const float* in, int Cin, __nv_bfloat16* out, int64_t HW, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / HW, pix = i - n * HW;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = c < Cin ? __ldg(in + (n * Cin + c) * HW + pix) : 0.f;
+        uint4 first; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&first);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) h[c] = __floats2bfloat162_rn(v[2 * c], v[2 * c + 1]);
+        uint4* dst = reinterpret_cast<uint4*>(out + i * 64);
+        dst[0] = first;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int c = 1; c < 8; ++c) dst[c] = z;
+    }
+}
+extern "C" int hd_pad_nchw(const float* in, int Cin, void* out, int N, int64_t HW, cudaStream_t stream) {
+    HD_REQUIRE(in && out && Cin > 0 && Cin <= 8 && N > 0 && HW > 0);
+    const int64_t total = (int64_t)N * HW;
+    int64_t blocks = (total + 255) / 256; if (blocks > (int64_t)hd_num_sms() * 16) blocks = (int64_t)hd_num_sms() * 16;
+    pad_nchw_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, Cin, (__nv_bfloat16*)out, HW, total);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }

@@ -32,6 +32,7 @@ struct ConvArgs {
     const T* res; T* out; float* out_nchw;             // out_nchw != null: fp32 NCHW output (tail)
     int Cout, P_out;
     int N, H, W, k;
+    int nchw_c;                                        // channels stored through out_nchw (<= Cout)
 };
 
 template <typename T>
@@ -67,7 +68,7 @@ __global__ void conv_simt_kernel(ConvArgs<T> a) {
         if (a.bias) acc += a.bias[co];
         if (a.emb) acc += a.emb[(int64_t)n * a.emb_stride + co];
         if (a.out_nchw) {
-            a.out_nchw[(((int64_t)n * a.Cout + co) * a.H + y) * a.W + x] = acc;
+            if (co < a.nchw_c) a.out_nchw[(((int64_t)n * a.nchw_c + co) * a.H + y) * a.W + x] = acc;
         } else {
             int64_t off = hd_view_off(a.Cout, a.P_out, a.H, a.W, n, y, x, co);
             if (a.res) acc += hd_ld(a.res + off);
@@ -84,20 +85,20 @@ extern "C" int hd_conv_simt(int dtype, const void* in0, int C0, const void* in1,
     HD_REQUIRE(ksize == 1 || ksize == 3);
     HD_REQUIRE(P_in == 1 || (P_in == 2 && C1 == 0 && !in_nchw_f32));
     HD_REQUIRE(P_out == 1 || (P_out == 2 && !out_nchw_f32 && !emb));
-    HD_REQUIRE(N > 0 && H > 0 && W > 0 && C0 > 0 && Cout > 0);
+    HD_REQUIRE(N > 0 && H > 0 && W > 0 && C0 > 0 && Cout > 0 && out_nchw_f32 >= 0 && out_nchw_f32 <= Cout);
     int64_t total = (int64_t)N * H * W * Cout * P_out * P_out;
     int block = 128;
     int grid = (int)((total + block - 1) / block < (int64_t)hd_num_sms() * 32 ? (total + block - 1) / block : (int64_t)hd_num_sms() * 32);
     if (dtype == HD_F32) {
         ConvArgs<float> a{in_nchw_f32 ? nullptr : (const float*)in0, (const float*)in1, in_nchw_f32 ? (const float*)in0 : nullptr, C0, C1, P_in,
                           (const float*)w, bias, emb, emb_stride, (const float*)res, out_nchw_f32 ? nullptr : (float*)out,
-                          out_nchw_f32 ? (float*)out : nullptr, Cout, P_out, N, H, W, ksize};
+                          out_nchw_f32 ? (float*)out : nullptr, Cout, P_out, N, H, W, ksize, out_nchw_f32};
         conv_simt_kernel<float><<<grid, block, 0, stream>>>(a);
     } else if (dtype == HD_BF16) {
         using B = __nv_bfloat16;
         ConvArgs<B> a{in_nchw_f32 ? nullptr : (const B*)in0, (const B*)in1, in_nchw_f32 ? (const float*)in0 : nullptr, C0, C1, P_in,
                       (const B*)w, bias, emb, emb_stride, (const B*)res, out_nchw_f32 ? nullptr : (B*)out,
-                      out_nchw_f32 ? (float*)out : nullptr, Cout, P_out, N, H, W, ksize};
+                      out_nchw_f32 ? (float*)out : nullptr, Cout, P_out, N, H, W, ksize, out_nchw_f32};
         conv_simt_kernel<B><<<grid, block, 0, stream>>>(a);
     } else { HD_REQUIRE(!"dtype"); }
     HD_CHECK_LAUNCH();
@@ -160,13 +161,13 @@ extern "C" int hd_wgrad_simt(int dtype, const void* in0, int C0, const void* in1
     int block = 128;
     if (dtype == HD_F32) {
         WgradArgs<float> a{{in_nchw_f32 ? nullptr : (const float*)in0, (const float*)in1, in_nchw_f32 ? (const float*)in0 : nullptr, C0, C1, P_in,
-                            nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 1, N, H, W, ksize},
+                            nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 1, N, H, W, ksize, 0},
                            dy_nchw_f32 ? nullptr : (const float*)dy, dy_nchw_f32 ? (const float*)dy : nullptr, Cdy, P_dy, dw, ppb};
         wgrad_simt_kernel<float><<<grid, block, 0, stream>>>(a);
     } else if (dtype == HD_BF16) {
         using B = __nv_bfloat16;
         WgradArgs<B> a{{in_nchw_f32 ? nullptr : (const B*)in0, (const B*)in1, in_nchw_f32 ? (const float*)in0 : nullptr, C0, C1, P_in,
-                        nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 1, N, H, W, ksize},
+                        nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, 1, N, H, W, ksize, 0},
                        dy_nchw_f32 ? nullptr : (const B*)dy, dy_nchw_f32 ? (const float*)dy : nullptr, Cdy, P_dy, dw, ppb};
         wgrad_simt_kernel<B><<<grid, block, 0, stream>>>(a);
     } else { HD_REQUIRE(!"dtype"); }

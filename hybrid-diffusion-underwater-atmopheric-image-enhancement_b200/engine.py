@@ -104,7 +104,7 @@ class ResBlock(nn.Module):
 class ConvSpec:
     """One logical stride-1 convolution (k in {1,3}) between views, with its packed weights."""
     __slots__ = ("name", "k", "CinL", "CoutL", "P_in", "P_out", "Cout", "Cin", "w_off", "wd_off", "b_off", "n_w", "has_bias",
-                 "_bias_inv", "_bias_same", "alg_frac")
+                 "_bias_inv", "_bias_same", "alg_frac", "real_cout")
 
     def __init__(self, name, k, Cin, Cout, P_in, P_out):
         self.name, self.k, self.Cin, self.Cout, self.P_in, self.P_out = name, k, Cin, Cout, P_in, P_out
@@ -114,6 +114,7 @@ class ConvSpec:
         self.has_bias = True
         # real reference taps / packed taps: DownSample packs 9 + 25 taps into 36 slots, ConvTranspose 25 into 36
         self.alg_frac = 34.0 / 36.0 if P_in == 2 else (25.0 / 36.0 if P_out == 2 else 1.0)
+        self.real_cout = Cout
 
 
 def _tbl_conv(off, Co, Ci, k):
@@ -294,14 +295,23 @@ class UNetBase(nn.Module):
             specs.append(spec)
             return spec
 
-        def conv_spec(name, m: nn.Conv2d):
+        def conv_spec(name, m: nn.Conv2d, pad_in=None, pad_out=None):
+            """pad_in / pad_out: GEMM widths of a zero-padded weight matrix (the 3-channel head / tail run on the
+            tcgen05 kernel as 64-channel convolutions; padded rows / columns are zero and receive no gradient)."""
             Co, Ci, k, _ = m.weight.shape
-            s = ConvSpec(name, k, Ci, Co, 1, 1)
-            bidx = torch.arange(Co, dtype=torch.int64) + O(m.bias)
-            return add(s, _tbl_conv(O(m.weight), Co, Ci, k), bias_a=bidx, bias_inv=[(O(m.bias), Co)])
+            CoP, CiP = pad_out or Co, pad_in or Ci
+            s = ConvSpec(name, k, CiP, CoP, 1, 1)
+            s.alg_frac = (Co * Ci) / float(CoP * CiP)
+            s.real_cout = Co
+            tbl = torch.full((CoP, k, k, CiP), -1, dtype=torch.int64)
+            tbl[:Co, :, :, :Ci] = _tbl_conv(O(m.weight), Co, Ci, k)
+            bidx = torch.full((CoP,), -1, dtype=torch.int64)
+            bidx[:Co] = torch.arange(Co, dtype=torch.int64) + O(m.bias)
+            return add(s, tbl, bias_a=bidx, bias_inv=[(O(m.bias), Co)])
 
-        st.head = conv_spec("head", self.head)
-        st.tail = conv_spec("tail", self.tail[2])
+        st.pad_io = self.compute_dtype == torch.bfloat16
+        st.head = conv_spec("head", self.head, pad_in=64 if st.pad_io else None)
+        st.tail = conv_spec("tail", self.tail[2], pad_out=64 if st.pad_io else None)
         st.blocks = {}
         for mod in list(self.downblocks) + list(self.middleblocks) + list(self.upblocks):
             b = {}
@@ -413,11 +423,12 @@ class UNetBase(nn.Module):
         else:
             N, H, W = x0.shape[0], x0.shape[1] // P_in, x0.shape[2] // P_in
         if out_nchw:
-            out = torch.empty((N, Cout, H, W), dtype=torch.float32, device=x0.device)
+            out = torch.empty((N, spec.real_cout, H, W), dtype=torch.float32, device=x0.device)
         else:
             out = torch.empty((N, H * P_out, W * P_out, Cout), dtype=self.compute_dtype, device=x0.device)
         ops.conv(x0, x1, P_in, self._wv(st, spec, dgrad), None if dgrad else self._bv(st, spec), emb, res, out, P_out,
-                 N, H, W, spec.k, in_nchw=in_nchw, out_nchw=out_nchw, alg_frac=spec.alg_frac)
+                 N, H, W, spec.k, in_nchw=in_nchw, out_nchw=out_nchw, alg_frac=spec.alg_frac,
+                 Cout_pad=Cout if out_nchw and Cout != spec.real_cout else None)
         return out
 
     def _wgrad(self, st, spec, x0, x1, dy, in_nchw=False, dy_nchw=False):
@@ -565,9 +576,15 @@ class UNetBase(nn.Module):
             ops.linear_fwd(cemb, w_c, b_c, emb_all, in_swish=True, accumulate=True)
             ctx.update(labels=labels, c0=c0, c1=c1, cemb=cemb)
         # ---- head ----
-        h = self._conv(st, st.head, x, in_nchw=True)
+        if st.pad_io:
+            xp = torch.empty((N, x.shape[2], x.shape[3], 64), dtype=self.compute_dtype, device=dev)
+            ops.pad_nchw(x, xp)
+            h = self._conv(st, st.head, xp)
+            ctx["x"] = xp
+        else:
+            h = self._conv(st, st.head, x, in_nchw=True)
+            ctx["x"] = x
         hs = [h]
-        ctx["x"] = x
         bctx = []
         ri = 0
         for mod in self.downblocks:
@@ -622,8 +639,14 @@ class UNetBase(nn.Module):
         f32 = dict(dtype=torch.float32, device=dev)
         d_emb_all = torch.zeros((N, st.emb_total), **f32)
         # ---- tail ----
-        self._wgrad(st, st.tail, ctx["tail_a"], None, d_eps, dy_nchw=True)
-        d_a = self._conv(st, st.tail, d_eps, dgrad=True, in_nchw=True)
+        if st.pad_io:
+            d_eps_p = torch.empty((N, d_eps.shape[2], d_eps.shape[3], 64), dtype=self.compute_dtype, device=dev)
+            ops.pad_nchw(d_eps, d_eps_p)
+            self._wgrad(st, st.tail, ctx["tail_a"], None, d_eps_p)
+            d_a = self._conv(st, st.tail, d_eps_p, dgrad=True)
+        else:
+            self._wgrad(st, st.tail, ctx["tail_a"], None, d_eps, dy_nchw=True)
+            d_a = self._conv(st, st.tail, d_eps, dgrad=True, in_nchw=True)
         d_h, _ = self._gn_bwd(st, ctx["tail_h"], None, self.tail[0], ctx["tail_sums"], 1, 0.0, 0, d_a)
         bctx = ctx["bctx"]
         mods = list(self.downblocks) + list(self.middleblocks) + list(self.upblocks)
@@ -655,7 +678,7 @@ class UNetBase(nn.Module):
             bctx[li] = None
         assert not dskip, "unconsumed skip gradients"
         # ---- head ----
-        self._wgrad(st, st.head, ctx["x"], None, d_h, in_nchw=True)
+        self._wgrad(st, st.head, ctx["x"], None, d_h, in_nchw=not st.pad_io)
         # ---- embedding path ----
         fg = st.flat_grad
         te = self.time_embedding.timembedding

@@ -53,7 +53,8 @@ class CudaOps:
         self.prof.setdefault(family, []).append((e0, e1, work))
 
     # ---- convolution family -------------------------------------------------------------
-    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0):
+    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0,
+             Cout_pad=None):
         """out = conv_k(view(x0|x1, P_in)) + bias + emb[:, :, None, None] + res, logical stride 1, 'same' padding.
         w: packed [CoutL][k*k][CinL] in the compute dtype.  H, W are the LOGICAL spatial dims.
         `alg_frac`: share of the packed taps that are real reference taps (space-to-depth views carry zeros);
@@ -62,21 +63,24 @@ class CudaOps:
         C0 = x0.shape[1] if in_nchw else x0.shape[-1]
         C1 = 0 if x1 is None else x1.shape[-1]
         Cout = out.shape[1] if out_nchw else out.shape[-1]
+        nchw_c = Cout if out_nchw else 0           # channels stored as fp32 NCHW (the 3-channel tail)
+        if Cout_pad is not None:
+            Cout = Cout_pad                        # GEMM width of a zero-padded weight matrix
         lib = self.lib
         e0 = self._t0()
         flops = 2.0 * N * H * W * (Cout * P_out * P_out) * k * k * ((C0 + C1) * P_in * P_in) * alg_frac
-        if (self.use_tc and dt == BF16 and not in_nchw and not out_nchw
+        if (self.use_tc and dt == BF16 and not in_nchw and nchw_c <= 16
                 and lib.hd_conv_tc_supported(C0, C1, P_in, Cout, P_out, H, W, k)):
             rc = lib.hd_conv_tc(_p(x0), C0, _p(x1), C1, P_in, _p(w), _p(bias), _p(emb),
                                 0 if emb is None else emb.stride(0), _p(res), _p(out), Cout, P_out,
-                                N, H, W, k, _stream())
+                                N, H, W, k, nchw_c, _stream())
             _lib.check(rc, "hd_conv_tc")
             self.launches += 1
             self.tc_launches += 1
             self._t1(e0, "conv_tc", flops)
             return
         rc = lib.hd_conv_simt(dt, _p(x0), C0, _p(x1), C1, P_in, int(in_nchw), _p(w), _p(bias), _p(emb),
-                              0 if emb is None else emb.stride(0), _p(res), _p(out), Cout, P_out, int(out_nchw),
+                              0 if emb is None else emb.stride(0), _p(res), _p(out), Cout, P_out, nchw_c,
                               N, H, W, k, _stream())
         _lib.check(rc, "hd_conv_simt")
         self.launches += 1
@@ -108,6 +112,12 @@ class CudaOps:
         _lib.check(rc, "hd_wgrad_simt")
         self.launches += 1
         self._t1(e0, "wgrad_simt", flops)
+
+    def pad_nchw(self, x, out):
+        """fp32 NCHW [N][C<=8][H][W] -> bf16 NHWC [N][H][W][64], zero-padded channels (input of the tcgen05 head conv)."""
+        N, C = x.shape[0], x.shape[1]
+        _lib.check(self.lib.hd_pad_nchw(_p(x), C, _p(out), N, x.shape[2] * x.shape[3], _stream()), "hd_pad_nchw")
+        self.launches += 1
 
     # ---- attention -----------------------------------------------------------------------
     def attn_fwd(self, qkv, out, lse, N, S, C):

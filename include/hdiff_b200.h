@@ -34,6 +34,7 @@ int hd_abi_version(void);
 /* ---- convolutions: nn.Conv2d / nn.ConvTranspose2d call sites DiffusionFreeGuidence/ModelCondition.py:71-72,
  *      82-83,96-99,130,144,147,219,251 and torch.cat :271; backward = autograd of the same (TrainCondition.py:60).
  *      Logical stride-1 'same' convolution, ksize in {1,3}, on views; w = packed [CoutL][ksize^2][CinL]. ---- */
+/* out_nchw_f32 = number of leading output channels stored as fp32 NCHW (0: NHWC in the activation dtype) */
 int hd_conv_simt(int dtype, const void* in0, int C0, const void* in1, int C1, int P_in, int in_nchw_f32,
                  const void* w, const float* bias, const float* emb, int64_t emb_stride, const void* res,
                  void* out, int Cout, int P_out, int out_nchw_f32, int N, int H, int W, int ksize, hd_stream_t stream);
@@ -44,7 +45,11 @@ int hd_wgrad_simt(int dtype, const void* in0, int C0, const void* in1, int C1, i
 int hd_conv_tc_supported(int C0, int C1, int P_in, int Cout, int P_out, int H, int W, int ksize);
 int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int P_in, const void* w, const float* bias,
                const float* emb, int64_t emb_stride, const void* res, void* out, int Cout, int P_out,
-               int N, int H, int W, int ksize, hd_stream_t stream);
+               int N, int H, int W, int ksize, int out_nchw_c, hd_stream_t stream);
+/* out_nchw_c > 0: `out` is fp32 NCHW [N][out_nchw_c][H][W] and only the first out_nchw_c output channels are stored
+ * (the 3-channel tail, ModelCondition.py:251, run as a 64-channel GEMM with zero-padded weights). */
+/* NCHW fp32 [N][Cin<=8][HW] -> NHWC bf16 [N][HW][64], channels >= Cin zero (head input / tail output gradient) */
+int hd_pad_nchw(const float* in, int Cin, void* out, int N, int64_t HW, hd_stream_t stream);
 /* K3 weight gradient: split over pixels, fp32 partials in `workspace`, deterministic second-stage reduce */
 int hd_wgrad_tc_supported(int C0, int C1, int P_in, int Cdy, int P_dy, int H, int W, int ksize);
 int64_t hd_wgrad_tc_workspace(int C0, int C1, int P_in, int Cdy, int P_dy, int N, int H, int W, int ksize);

@@ -46,7 +46,7 @@ class EmuOps:
         x = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
         return to_logical(x, P_in).permute(0, 3, 1, 2).float()
 
-    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0):
+    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0, Cout_pad=None):
         xin = self._logical_in(x0, x1, P_in, in_nchw)
         CinL = xin.shape[1]
         CoutL = w.numel() // (k * k * CinL)
@@ -55,7 +55,7 @@ class EmuOps:
         if emb is not None:
             y = y + emb.float()[:, :, None, None]
         if out_nchw:
-            out.copy_(y)
+            out.copy_(y[:, :out.shape[1]])
         else:
             y = from_logical(y.permute(0, 2, 3, 1), P_out)
             if res is not None:
@@ -69,6 +69,11 @@ class EmuOps:
         CinL, CoutL = xin.shape[1], g.shape[1]
         gw = torch.nn.grad.conv2d_weight(xin, (CoutL, CinL, k, k), g, padding=k // 2)
         dw.copy_(gw.permute(0, 2, 3, 1).reshape(-1))
+        self.launches += 1
+
+    def pad_nchw(self, x, out):
+        out.zero_()
+        out[..., :x.shape[1]] = x.permute(0, 2, 3, 1).to(out.dtype)
         self.launches += 1
 
     # ---- attention ----

@@ -145,3 +145,29 @@ def test_second_backward_without_zero_grad_accumulates():
     g1 = net.head.weight.grad.clone()
     net(x, t).sum().backward()
     assert torch.allclose(net.head.weight.grad, 2 * g1, rtol=1e-5, atol=1e-7)
+
+
+def test_bf16_schedule_with_padded_head_and_tail_vs_oracle():
+    """bf16 compute mode routes the 3-channel head / tail through 64-channel GEMM operands (zero-padded packed weights,
+    channel-padded NHWC input, fp32 NCHW store of the first 3 output channels).  The index tables of that path are
+    checked here against the oracle (tolerance = bf16 storage of activations and weights)."""
+    cfg = dict(T=50, ch=32, ch_mult=[1, 2], attn=[1], num_res_blocks=1, dropout=0.0)
+    torch.manual_seed(9)
+    ref = R.UNet(num_labels=None, **cfg)
+    net = UNetU(compute_dtype=torch.bfloat16, **cfg)
+    net.load_state_dict(ref.state_dict())
+    x = torch.randn(2, 3, 16, 16)
+    t = torch.tensor([7, 33])
+    e_ref = ref(x, t)
+    e = net(x, t)
+    assert e.dtype == torch.float32 and e.shape == e_ref.shape
+    assert _rel(e.detach(), e_ref.detach()) < 2e-2
+    gy = torch.randn_like(e_ref)
+    e_ref.backward(gy)
+    e.backward(gy)
+    pr = dict(ref.named_parameters())
+    gscale = max(float(p.grad.norm()) for p in pr.values() if p.grad is not None)
+    for k in ("head.weight", "head.bias", "tail.2.weight", "tail.2.bias", "tail.0.weight"):
+        p = dict(net.named_parameters())[k]
+        assert p.grad.shape == pr[k].grad.shape
+        assert _close(p.grad, pr[k].grad, 5e-2, 1e-3 * gscale), (k, _rel(p.grad, pr[k].grad))
