@@ -215,7 +215,7 @@ class UNetBase(nn.Module):
         self._state = None       # built lazily on the parameters' device
         self._frozen = False
         self.dp_group = None     # set by hdiff_b200.parallel.enable_data_parallel
-        self.dp_bucket_bytes = 32 << 20
+        self.dp_bucket_bytes = 8 << 20
 
     # -----------------------------------------------------------------------------------------
     # flat buffers + packed layouts
@@ -233,12 +233,18 @@ class UNetBase(nn.Module):
         order += [rb.cond_proj[1].weight for rb in rbs]
         order += [rb.cond_proj[1].bias for rb in rbs]
         seen = {id(p) for p in order}
-        order += [p for p in named.values() if id(p) not in seen]
+        # convolution parameters last: their gradients are produced in packed form (gpk) and all-reduced there, so
+        # the data-parallel exchange of the flat buffer only covers the prefix [0, n_direct)
+        conv_ids = {id(p) for m in self.modules() if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)) for p in m.parameters()}
+        order += [p for p in named.values() if id(p) not in seen and id(p) not in conv_ids]
+        n_direct_params = len(order)
+        order += [p for p in named.values() if id(p) not in seen and id(p) in conv_ids]
         offs, off = {}, 0
         for p in order:
             offs[id(p)] = off
             off += (p.numel() + 3) // 4 * 4      # keep every parameter 16-byte aligned
         n_flat = off
+        n_direct = offs[id(order[n_direct_params])] if n_direct_params < len(order) else n_flat
         flat = torch.zeros(n_flat, dtype=torch.float32, device=dev)
         with torch.no_grad():
             for p in order:
@@ -247,6 +253,7 @@ class UNetBase(nn.Module):
                 p.data = flat[o:o + p.numel()].view(p.shape)
         st = _State()
         st.device, st.flat, st.n_flat, st.offs, st.order = dev, flat, n_flat, offs, order
+        st.n_direct = n_direct
         st.ptrs = [p.data_ptr() for p in order]
         st.flat_grad = None
         O = lambda p: offs[id(p)]
@@ -313,6 +320,7 @@ class UNetBase(nn.Module):
         st.head = conv_spec("head", self.head, pad_in=64 if st.pad_io else None)
         st.tail = conv_spec("tail", self.tail[2], pad_out=64 if st.pad_io else None)
         st.blocks = {}
+        st.block_lo = {}
         for mod in list(self.downblocks) + list(self.middleblocks) + list(self.upblocks):
             b = {}
             if isinstance(mod, ResBlock):
@@ -344,6 +352,7 @@ class UNetBase(nn.Module):
                                  bias_inv=[(O(mod.t.bias), C)])
                 b["conv"] = conv_spec("conv", mod.c)
             st.blocks[id(mod)] = b
+            st.block_lo[id(mod)] = min(sp.w_off for sp in b.values()) // 2
         st.specs = specs
         st.n_wpack = wcur[0]
         st.n_dw = wcur[0] // 2
@@ -638,6 +647,12 @@ class UNetBase(nn.Module):
         st.gpk[st.n_dw:].zero_()
         f32 = dict(dtype=torch.float32, device=dev)
         d_emb_all = torch.zeros((N, st.emb_total), **f32)
+        reducer = None
+        if self.dp_group is not None:
+            from . import parallel
+            reducer = parallel.GradReducer(self.dp_group, self.dp_bucket_bytes)
+            reducer.attach(st.gpk, st.n_dw)
+            self.last_reducer = reducer
         # ---- tail ----
         if st.pad_io:
             d_eps_p = torch.empty((N, d_eps.shape[2], d_eps.shape[3], 64), dtype=self.compute_dtype, device=dev)
@@ -676,6 +691,8 @@ class UNetBase(nn.Module):
                 self._wgrad(st, sp["convT"], c["x"], None, d_u)
                 d_h = self._conv(st, sp["convT"], d_u, dgrad=True)
             bctx[li] = None
+            if reducer is not None:
+                reducer.ready(st.block_lo[id(mod)])      # weight gradients of this and all later blocks are final
         assert not dskip, "unconsumed skip gradients"
         # ---- head ----
         self._wgrad(st, st.head, ctx["x"], None, d_h, in_nchw=not st.pad_io)
@@ -709,12 +726,12 @@ class UNetBase(nn.Module):
             d_c0 = torch.empty_like(c0)
             ops.linear_bwd_x(d_c1, ce[1].weight, None, d_c0)
             ops.embedding_bwd(d_c0, ctx["labels"], gv(ce[0].weight), padding_idx=0)
+        # ---- data parallel: the rest of the packed weight gradients (head / tail / first blocks), the packed bias
+        #      gradients and the directly written part of the flat buffer; then the compute stream waits ----
+        if reducer is not None:
+            reducer.finish(st.gpk[st.n_dw:], fg[:st.n_direct])
         # ---- packed conv gradients -> parameter layouts ----
         ops.scatter_unpack(st.gpk, st.inv, fg)
-        # ---- data parallel: mean over ranks, flat buckets ----
-        if self.dp_group is not None:
-            from . import parallel
-            parallel.allreduce_flat_(fg, self.dp_group, self.dp_bucket_bytes)
         used_cond = "labels" in ctx
         grads = []
         for p in st.order:

@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 
-def enable_data_parallel(net, group=None, bucket_bytes=64 << 20, broadcast=True):
+def enable_data_parallel(net, group=None, bucket_bytes=8 << 20, broadcast=True):
     """Attach a process group to a hdiff_b200 UNet.  Parameters are broadcast from rank 0 once."""
     assert dist.is_initialized(), "init torch.distributed first (backend nccl on GPUs, gloo on CPU tests)"
     group = group if group is not None else dist.group.WORLD
@@ -27,18 +27,62 @@ def enable_data_parallel(net, group=None, bucket_bytes=64 << 20, broadcast=True)
 
 def allreduce_flat_(flat_grad: torch.Tensor, group, bucket_bytes: int):
     """In-place mean over the ranks of `group`, bucketed; asynchronous with respect to the host."""
-    world = dist.get_world_size(group)
-    if world == 1:
-        return
+    red = GradReducer(group, bucket_bytes)
     n = flat_grad.numel()
     step = max(1, bucket_bytes // 4)
-    works = []
     for lo in range(0, n, step):
-        chunk = flat_grad[lo:lo + step]
-        chunk.mul_(1.0 / world)
-        works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=group, async_op=True))
-    for w in works:
-        w.wait()          # stream dependency only (NCCL): the compute stream waits, the host does not
+        red.reduce_async(flat_grad[lo:lo + step])
+    red.wait()
+
+
+class GradReducer:
+    """Bucketed mean all-reduce overlapped with the backward pass.
+
+    The UNet's backward schedule calls `ready(lo)` every time the packed weight-gradient buffer is final from
+    offset `lo` to its end (blocks finish in reverse order, and the buffer is laid out in block order, so the
+    finished region is a growing suffix).  Whenever at least one bucket of finished bytes has accumulated it is
+    all-reduced asynchronously: NCCL runs on its own stream behind the kernels already enqueued and under the ones
+    that follow.  `finish()` reduces what is left and makes the compute stream wait for all of it."""
+
+    def __init__(self, group, bucket_bytes: int):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.bucket = max(1, int(bucket_bytes) // 4)
+        self.works = []
+        self.buf = None
+        self.hi = 0
+        self.launched = 0                      # number of collectives issued (tests / bench read it)
+
+    def reduce_async(self, chunk: torch.Tensor):
+        if self.world == 1 or chunk.numel() == 0:
+            return
+        chunk.mul_(1.0 / self.world)
+        self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.launched += 1
+
+    def attach(self, buf: torch.Tensor, hi: int):
+        """`buf[:hi]` is the region that `ready()` walks down."""
+        self.buf, self.hi = buf, hi
+
+    def ready(self, lo: int):
+        if self.hi - lo >= self.bucket:
+            self.reduce_async(self.buf[lo:self.hi])
+            self.hi = lo
+
+    def finish(self, *extra: torch.Tensor):
+        if self.buf is not None and self.hi > 0:
+            self.reduce_async(self.buf[:self.hi])
+            self.hi = 0
+        for t in extra:
+            n = t.numel()
+            for lo in range(0, n, self.bucket):
+                self.reduce_async(t[lo:lo + self.bucket])
+        self.wait()
+
+    def wait(self):
+        for w in self.works:
+            w.wait()      # stream dependency only (NCCL): the compute stream waits, the host does not
+        self.works = []
 
 
 def shard_batch(x, rank, world):

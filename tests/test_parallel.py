@@ -1,0 +1,79 @@
+"""Data-parallel path on CPU: two `gloo` ranks, the torch test double of the operator layer standing in for the CUDA
+library.  Checks the one exchange of the path: after backward every rank holds the MEAN over ranks of
+the per-rank gradients — equal to the single-process gradient of the concatenated batch divided by the world size —
+with the packed weight-gradient buffer reduced in several overlapped buckets, plus the batch sharding of sampling."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    import hdiff_b200.ops as hops
+    from hdiff_b200 import parallel
+    from hdiff_b200.DiffusionFreeGuidence.ModelCondition import UNet
+    from tests.emu_backend import EmuOps
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    hops.set_backend(EmuOps())
+    cfg = dict(T=50, ch=32, ch_mult=[1, 2], attn=[1], num_res_blocks=1, dropout=0.0)
+    torch.manual_seed(123 + rank)                 # different initial weights per rank: the broadcast must fix that
+    net = UNet(num_labels=4, compute_dtype=torch.float32, **cfg)
+    parallel.enable_data_parallel(net, bucket_bytes=256 << 10)
+    torch.manual_seed(7)
+    x = torch.randn(4, 3, 16, 16)
+    t = torch.tensor([3, 9, 20, 41])
+    lab = torch.tensor([1, 0, 4, 2])
+    gy = torch.randn(4, 3, 16, 16)
+    xs = parallel.shard_batch(x, rank, world)
+    sl = slice(rank * 2, rank * 2 + 2)
+    assert torch.equal(xs, x[sl])
+    net(xs, t[sl], lab[sl]).backward(gy[sl])
+    n_coll = net.last_reducer.launched
+    got = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    # single-process reference on the full batch, same weights, no process group
+    ref = UNet(num_labels=4, compute_dtype=torch.float32, **cfg)
+    ref.load_state_dict(sd)
+    ref(x, t, lab).backward(gy)
+    worst = 0.0
+    for k, p in ref.named_parameters():
+        if p.grad is None:
+            continue
+        d = float((got[k] - p.grad / world).norm())
+        worst = max(worst, d / (float(p.grad.norm()) / world + 1e-6))
+    q.put((rank, worst, n_coll, float(sd["head.weight"].sum())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gradient_mean_matches_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    assert abs(res[0][3] - res[1][3]) < 1e-6, "parameters were not broadcast from rank 0"
+    for rank, worst, n_coll, _ in res:
+        assert worst < 2e-4, (rank, worst)
+        assert n_coll >= 3, "expected several overlapped buckets plus the tail exchange"
