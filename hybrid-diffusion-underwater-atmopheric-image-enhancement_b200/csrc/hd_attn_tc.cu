@@ -232,8 +232,12 @@ struct AttnBwdParams {
     __nv_bfloat16* dqkv;
 };
 
+// 8 element-wise warps: two per TMEM lane quarter, each owning 32 of the 64 score columns of a tile (a single warp per
+// scheduler cannot hide the MUFU / TMEM-load latencies of 128 values per thread and would leave the tensor pipe idle)
+constexpr int kBwdThreads = 64 + 256;
+
 template <bool kDQ>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO, const AttnBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -260,7 +264,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         tma_prefetch_desc(&mapQKV); tma_prefetch_desc(&mapDO);
         mbar_init(x_full, 1);
         for (int s = 0; s < kBwdStages; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-        mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(acc_done, 1);
+        mbar_init(s_full, 1); mbar_init(s_empty, 8); mbar_init(p_full, 8); mbar_init(acc_done, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -342,6 +346,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         }
     } else {
         const int quarter = warp & 3;
+        const int h = (warp - 2) >> 2;               // which 32 of the 64 score columns this warp owns
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const float sl2 = p.scale_log2;
@@ -352,35 +357,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             const uint32_t tPd = lane_base + kColPd + (j & 1) * 64;
+            uint32_t sv[32], dv[32];
+            tmem_ld32(lane_base + kColSt + h * 32, sv);
+            tmem_ld32(lane_base + kColdPt + h * 32, dv);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);     // this warp's share of the score columns is in registers
+            uint32_t pp[16], ds[16];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t sv[32], dv[32];
-                tmem_ld32(lane_base + kColSt + h * 32, sv);
-                tmem_ld32(lane_base + kColdPt + h * 32, dv);
-                tmem_wait_ld();
-                if (h == 1) {                      // both halves are in registers: the score columns are free
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(s_empty);
+            for (int i = 0; i < 16; ++i) {
+                float2 s0 = my, s1 = my;
+                if (!kDQ) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(stats_n + j * BN + h * 32 + 2 * i));
+                    s0 = make_float2(q.x, q.y); s1 = make_float2(q.z, q.w);
                 }
-                uint32_t pp[16], ds[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float2 s0 = my, s1 = my;
-                    if (!kDQ) {
-                        const float4 q = __ldg(reinterpret_cast<const float4*>(stats_n + j * BN + h * 32 + 2 * i));
-                        s0 = make_float2(q.x, q.y); s1 = make_float2(q.z, q.w);
-                    }
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * i]), sl2, -s0.x));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -s1.x));
-                    const float d0 = p0 * (__uint_as_float(dv[2 * i]) - s0.y);
-                    const float d1 = p1 * (__uint_as_float(dv[2 * i + 1]) - s1.y);
-                    pp[i] = pack_bf16x2(p0, p1);
-                    ds[i] = pack_bf16x2(d0, d1);
-                }
-                tmem_st16(tPd + h * 16, ds);
-                if (!kDQ) tmem_st16(tPd + 32 + h * 16, pp);
+                const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * i]), sl2, -s0.x));
+                const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -s1.x));
+                const float d0 = p0 * (__uint_as_float(dv[2 * i]) - s0.y);
+                const float d1 = p1 * (__uint_as_float(dv[2 * i + 1]) - s1.y);
+                pp[i] = pack_bf16x2(p0, p1);
+                ds[i] = pack_bf16x2(d0, d1);
             }
+            tmem_st16(tPd + h * 16, ds);
+            if (!kDQ) tmem_st16(tPd + 32 + h * 16, pp);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -393,7 +393,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         for (int a = 0; a < (kDQ ? 1 : 2); ++a) {
             const float mul = a == 0 ? p.scale : 1.f;
 #pragma unroll 1
-            for (int c = 0; c < D; c += 32) {
+            for (int c = h * 64; c < h * 64 + 64; c += 32) {     // the two warps of a lane quarter split the 128 columns
                 uint32_t o[32];
                 tmem_ld32(lane_base + (a == 0 ? kColAcc0 : kColAcc1) + c, o);
                 tmem_wait_ld();
@@ -484,9 +484,9 @@ extern "C" int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout
         }
         attr_set = true;
     }
-    attn_bwd_tc_kernel<false><<<dim3(S / BM, N), kThreads, smem, stream>>>(mQKV, mDO, p);
+    attn_bwd_tc_kernel<false><<<dim3(S / BM, N), kBwdThreads, smem, stream>>>(mQKV, mDO, p);
     HD_CHECK_LAUNCH();
-    attn_bwd_tc_kernel<true><<<dim3(S / BM, N), kThreads, smem, stream>>>(mQKV, mDO, p);
+    attn_bwd_tc_kernel<true><<<dim3(S / BM, N), kBwdThreads, smem, stream>>>(mQKV, mDO, p);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }

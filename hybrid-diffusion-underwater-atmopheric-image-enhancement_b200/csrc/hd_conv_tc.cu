@@ -65,18 +65,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int tx_i = m_tile % p.tiles_x; const int r = m_tile / p.tiles_x;
                 const int ty_i = r % p.tiles_y; const int n = r / p.tiles_y;
                 const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
-                    const int cc = kb % p.nchunk_c; const int r2 = kb / p.nchunk_c;
-                    const int py = r2 % p.P_in; const int tap = r2 / p.P_in;
-                    const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    if (cc < p.nchunk0) tma_load_5d(sa, &mapA0, &full[stage], cc * 64, x0 + dx, py, y0 + dy, n);
-                    else tma_load_5d(sa, &mapA1, &full[stage], (cc - p.nchunk0) * 64, x0 + dx, py, y0 + dy, n);
-                    tma_load_2d(sa + kABytes, &mapB, &full[stage], kb * 64, n_tile * p.NT);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                }
+                // K order = (tap row, tap column, parity row, 64-channel chunk); plain counters, no divisions: this
+                // single thread's loop rate bounds how fast shared memory can be filled
+                int kb = 0;
+                for (int ty = 0; ty < p.k; ++ty)
+                    for (int tx = 0; tx < p.k; ++tx)
+                        for (int py = 0; py < p.P_in; ++py)
+                            for (int cc = 0; cc < p.nchunk_c; ++cc, ++kb) {
+                                mbar_wait(&empty[stage], phase ^ 1);
+                                mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                                if (cc < p.nchunk0) tma_load_5d(sa, &mapA0, &full[stage], cc * 64, x0 + tx - p.pad, py, y0 + ty - p.pad, n);
+                                else tma_load_5d(sa, &mapA1, &full[stage], (cc - p.nchunk0) * 64, x0 + tx - p.pad, py, y0 + ty - p.pad, n);
+                                tma_load_2d(sa + kABytes, &mapB, &full[stage], kb * 64, n_tile * p.NT);
+                                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            }
             }
         }
     } else if (warp == 1) {

@@ -14,10 +14,10 @@ template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; using raw = 
 
 template <typename T> __device__ __forceinline__ void vec_load(const T* p, float* v);
 template <> __device__ __forceinline__ void vec_load<float>(const float* p, float* v) {
-    float4 r = *reinterpret_cast<const float4*>(p); v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+    float4 r = __ldg(reinterpret_cast<const float4*>(p)); v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
 }
 template <> __device__ __forceinline__ void vec_load<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
-    uint4 r = *reinterpret_cast<const uint4*>(p);
+    uint4 r = __ldg(reinterpret_cast<const uint4*>(p));      // read-only path: loads may be hoisted above earlier stores
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(Src2<T> x, int N, int64_t
     if (sub < ppi) {
         const int64_t p0 = blockIdx.x * pix_per_block;
         const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
+#pragma unroll 4
         for (int64_t p = p0 + sub; p < p1; p += ppi) {
             float v[V]; vec_load(x.at(n, p, HW, lane * V), v);
 #pragma unroll
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> x, GnParams g, in
     const int64_t p0 = blockIdx.x * pix_per_block;
     const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
     const bool drop = g.p_drop > 0.f;
+#pragma unroll 4
     for (int64_t pix = p0 + sub; pix < p1; pix += ppi) {
         float v[V]; vec_load(x.at(n, pix, g.HW, c0), v);
         const int64_t obase = ((int64_t)n * g.HW + pix) * g.C + c0;
@@ -209,26 +211,31 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams 
     const int lane = threadIdx.x % lanes, sub = threadIdx.x / lanes;
     if (sub < ppi) {
         const int c0 = lane * V;
-        float gam[V], bet[V], s1[V], s2[V];
+        float gam[V], bet[V], s1[V], s2[V], rs[V], mr[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) { gam[k] = g.gamma[c0 + k]; bet[k] = g.beta[c0 + k]; s1[k] = 0.f; s2[k] = 0.f; }
+        for (int k = 0; k < V; ++k) {
+            const int gi = (c0 + k) / cpg;
+            gam[k] = g.gamma[c0 + k]; bet[k] = g.beta[c0 + k]; s1[k] = 0.f; s2[k] = 0.f;
+            rs[k] = s_rstd[gi]; mr[k] = -s_mean[gi] * s_rstd[gi];
+        }
+        const bool drop = g.p_drop > 0.f;
         const int64_t p0 = blockIdx.x * pix_per_block;
         const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
+#pragma unroll 2
         for (int64_t p = p0 + sub; p < p1; p += ppi) {
             float v[V], d[V];
             vec_load(x.at(n, p, g.HW, c0), v);
             const int64_t obase = ((int64_t)n * g.HW + p) * g.C + c0;
             vec_load(dy + obase, d);
             float ds[V];
-            if (g.p_drop > 0.f) hd_dropout_vec<V>(g.seed, (uint64_t)obase, g.p_drop, ds);
+            if (drop) hd_dropout_vec<V>(g.seed, (uint64_t)obase, g.p_drop, ds);
 #pragma unroll
             for (int k = 0; k < V; ++k) {
-                int gi = (c0 + k) / cpg;
-                float xh = (v[k] - s_mean[gi]) * s_rstd[gi];
+                const float xh = fmaf(v[k], rs[k], mr[k]);
                 float dd = d[k];
-                if (g.p_drop > 0.f) dd *= ds[k];
-                if (g.act) dd *= hd_swish_grad(xh * gam[k] + bet[k]);
-                s1[k] += dd; s2[k] += dd * xh;
+                if (drop) dd *= ds[k];
+                if (g.act) dd *= hd_swish_grad(fmaf(xh, gam[k], bet[k]));
+                s1[k] += dd; s2[k] = fmaf(dd, xh, s2[k]);
             }
         }
 #pragma unroll
@@ -302,6 +309,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g
     const int64_t p0 = blockIdx.x * pix_per_block;
     const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
     const bool drop = g.p_drop > 0.f;
+#pragma unroll 2
     for (int64_t pix = p0 + sub; pix < p1; pix += ppi) {
         float v[V], d[V], r[V];
         vec_load(x.at(n, pix, g.HW, c0), v);
@@ -365,6 +373,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* t, int N, int64_t 
         for (int k = 0; k < V; ++k) s[k] = 0.f;
         const int64_t p0 = blockIdx.x * pix_per_block;
         const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
+    #pragma unroll 4
         for (int64_t p = p0 + sub; p < p1; p += ppi) {
             float v[V]; vec_load(t + ((int64_t)n * HW + p) * C + lane * V, v);
 #pragma unroll

@@ -65,28 +65,41 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
     if (warp == 0) {
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
+            // the (tap, parity, chunk) coordinates of this CTA's operand blocks do not depend on the pixel tile: decode
+            // them once (the divisions below used to sit in the per-tile loop of this single thread)
+            constexpr int kMaxBlk = 8;
+            int a_c[kMaxBlk], a_py[kMaxBlk], a_dy[kMaxBlk], a_dx[kMaxBlk];
+#pragma unroll
+            for (int b = 0; b < kMaxBlk; ++b) {
+                int blk = group * 2 * p.G + b;
+                if (blk >= p.nblocks) blk = p.nblocks - 1;               // padding rows: duplicate, discarded later
+                const int cc = blk % p.nchunk_c; const int r2 = blk / p.nchunk_c;
+                a_c[b] = cc; a_py[b] = r2 % p.P_in;
+                const int tap = r2 / p.P_in;
+                a_dy[b] = tap / p.k - p.pad; a_dx[b] = tap % p.k - p.pad;
+            }
+            const int dy_c0 = (n_tile * p.nb) % p.nch_dy, dy_py0 = (n_tile * p.nb) / p.nch_dy;
+            int tx_i = t_begin % p.tiles_x; int r = t_begin / p.tiles_x;
+            int ty_i = r % p.tiles_y; int n = r / p.tiles_y;
             for (int t = t_begin; t < t_end; ++t) {
-                const int tx_i = t % p.tiles_x; const int r = t / p.tiles_x;
-                const int ty_i = r % p.tiles_y; const int n = r / p.tiles_y;
                 const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
                 mbar_wait(&empty[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                for (int b = 0; b < 2 * p.G; ++b) {
-                    int blk = group * 2 * p.G + b;
-                    if (blk >= p.nblocks) blk = p.nblocks - 1;           // padding rows: duplicate, discarded later
-                    const int cc = blk % p.nchunk_c; const int r2 = blk / p.nchunk_c;
-                    const int py = r2 % p.P_in; const int tap = r2 / p.P_in;
-                    const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
-                    if (cc < p.nchunk0) tma_load_5d(sa + b * kBlkBytes, &mapX0, &full[stage], cc * 64, x0 + dx, py, y0 + dy, n);
-                    else tma_load_5d(sa + b * kBlkBytes, &mapX1, &full[stage], (cc - p.nchunk0) * 64, x0 + dx, py, y0 + dy, n);
+#pragma unroll
+                for (int b = 0; b < kMaxBlk; ++b) {
+                    if (b < 2 * p.G) {
+                        if (a_c[b] < p.nchunk0) tma_load_5d(sa + b * kBlkBytes, &mapX0, &full[stage], a_c[b] * 64, x0 + a_dx[b], a_py[b], y0 + a_dy[b], n);
+                        else tma_load_5d(sa + b * kBlkBytes, &mapX1, &full[stage], (a_c[b] - p.nchunk0) * 64, x0 + a_dx[b], a_py[b], y0 + a_dy[b], n);
+                    }
                 }
+                int cc = dy_c0, py = dy_py0;
                 for (int b = 0; b < p.nb; ++b) {
-                    const int blk = n_tile * p.nb + b;
-                    const int cc = blk % p.nch_dy, py = blk / p.nch_dy;
                     tma_load_5d(sa + a_bytes + b * kBlkBytes, &mapDY, &full[stage], cc * 64, x0, py, y0, n);
+                    if (++cc == p.nch_dy) { cc = 0; ++py; }
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                if (++tx_i == p.tiles_x) { tx_i = 0; if (++ty_i == p.tiles_y) { ty_i = 0; ++n; } }
             }
         }
     } else if (warp == 1) {
