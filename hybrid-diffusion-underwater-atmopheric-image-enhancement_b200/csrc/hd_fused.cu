@@ -22,6 +22,18 @@ template <> __device__ __forceinline__ void vec_load<__nv_bfloat16>(const __nv_b
 #pragma unroll
     for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
+// raw (still packed) vector loads: issued in batches BEFORE any of them is unpacked, so that every thread keeps several
+// 16-byte requests in flight (these kernels are latency-bound otherwise: ~16 KB in flight per SM against the ~45 KB
+// that 6.5 TB/s needs)
+template <typename T> __device__ __forceinline__ typename Vec<T>::raw raw_load(const T* p) {
+    return __ldg(reinterpret_cast<const typename Vec<T>::raw*>(p));
+}
+__device__ __forceinline__ void unpack(const float4& r, float* v) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+__device__ __forceinline__ void unpack(const uint4& r, float* v) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
 template <typename T> __device__ __forceinline__ void vec_store(T* p, const float* v);
 template <> __device__ __forceinline__ void vec_store<float>(float* p, const float* v) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -77,11 +89,17 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(Src2<T> x, int N, int64_t
     if (sub < ppi) {
         const int64_t p0 = blockIdx.x * pix_per_block;
         const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
-#pragma unroll 4
-        for (int64_t p = p0 + sub; p < p1; p += ppi) {
-            float v[V]; vec_load(x.at(n, p, HW, lane * V), v);
+        constexpr int U = 4;
+        for (int64_t p = p0 + sub; p < p1; p += (int64_t)U * ppi) {
+            typename Vec<T>::raw xr[U];
 #pragma unroll
-            for (int i = 0; i < V; ++i) { s[i] += v[i]; ss[i] += v[i] * v[i]; }
+            for (int u = 0; u < U; ++u) if (p + (int64_t)u * ppi < p1) xr[u] = raw_load(x.at(n, p + (int64_t)u * ppi, HW, lane * V));
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (p + (int64_t)u * ppi < p1) {
+                float v[V]; unpack(xr[u], v);
+#pragma unroll
+                for (int i = 0; i < V; ++i) { s[i] += v[i]; ss[i] += v[i] * v[i]; }
+            }
         }
 #pragma unroll
         for (int i = 0; i < V; ++i) { int g = (lane * V + i) / cpg; atomicAdd(&sg[g][0], s[i]); atomicAdd(&sg[g][1], ss[i]); }
@@ -157,20 +175,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> x, GnParams g, in
     const int64_t p0 = blockIdx.x * pix_per_block;
     const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
     const bool drop = g.p_drop > 0.f;
-#pragma unroll 4
-    for (int64_t pix = p0 + sub; pix < p1; pix += ppi) {
-        float v[V]; vec_load(x.at(n, pix, g.HW, c0), v);
-        const int64_t obase = ((int64_t)n * g.HW + pix) * g.C + c0;
-        float ds[V];
-        if (drop) hd_dropout_vec<V>(g.seed, (uint64_t)obase, g.p_drop, ds);
+    constexpr int U = 4;
+    for (int64_t pb = p0 + sub; pb < p1; pb += (int64_t)U * ppi) {
+        typename Vec<T>::raw xr[U];
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-            float z = fmaf(v[k], a[k], b[k]);
-            if (g.act) z = hd_swish(z);
-            if (drop) z *= ds[k];
-            v[k] = z;
+        for (int u = 0; u < U; ++u) if (pb + (int64_t)u * ppi < p1) xr[u] = raw_load(x.at(n, pb + (int64_t)u * ppi, g.HW, c0));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t pix = pb + (int64_t)u * ppi;
+            if (pix < p1) {
+                float v[V]; unpack(xr[u], v);
+                const int64_t obase = ((int64_t)n * g.HW + pix) * g.C + c0;
+                float ds[V];
+                if (drop) hd_dropout_vec<V>(g.seed, (uint64_t)obase, g.p_drop, ds);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    float z = fmaf(v[k], a[k], b[k]);
+                    if (g.act) z = hd_swish(z);
+                    if (drop) z *= ds[k];
+                    v[k] = z;
+                }
+                vec_store(out + obase, v);
+            }
         }
-        vec_store(out + obase, v);
     }
 }
 template <typename T>
@@ -211,38 +238,52 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams 
     const int lane = threadIdx.x % lanes, sub = threadIdx.x / lanes;
     if (sub < ppi) {
         const int c0 = lane * V;
-        float gam[V], bet[V], s1[V], s2[V], rs[V], mr[V];
+        // z = v*A1 + B1 is the pre-activation; the sums kept per thread are sum(dy') and sum(dy' * v): xhat = v*rstd - mean*rstd
+        // is applied once at the end (fewer live registers -> more loads in flight)
+        float A1[V], B1[V], s1[V], s2[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const int gi = (c0 + k) / cpg;
-            gam[k] = g.gamma[c0 + k]; bet[k] = g.beta[c0 + k]; s1[k] = 0.f; s2[k] = 0.f;
-            rs[k] = s_rstd[gi]; mr[k] = -s_mean[gi] * s_rstd[gi];
+            A1[k] = s_rstd[gi] * g.gamma[c0 + k];
+            B1[k] = g.beta[c0 + k] - s_mean[gi] * A1[k];
+            s1[k] = 0.f; s2[k] = 0.f;
         }
         const bool drop = g.p_drop > 0.f;
         const int64_t p0 = blockIdx.x * pix_per_block;
         const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
-#pragma unroll 2
-        for (int64_t p = p0 + sub; p < p1; p += ppi) {
+        constexpr int U = 4;
+        for (int64_t pb = p0 + sub; pb < p1; pb += (int64_t)U * ppi) {
+          typename Vec<T>::raw xr[U], dr[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) if (pb + (int64_t)u * ppi < p1) {
+              xr[u] = raw_load(x.at(n, pb + (int64_t)u * ppi, g.HW, c0));
+              dr[u] = raw_load(dy + ((int64_t)n * g.HW + pb + (int64_t)u * ppi) * g.C + c0);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) if (pb + (int64_t)u * ppi < p1) {
+            const int64_t p = pb + (int64_t)u * ppi;
             float v[V], d[V];
-            vec_load(x.at(n, p, g.HW, c0), v);
+            unpack(xr[u], v);
             const int64_t obase = ((int64_t)n * g.HW + p) * g.C + c0;
-            vec_load(dy + obase, d);
+            unpack(dr[u], d);
             float ds[V];
             if (drop) hd_dropout_vec<V>(g.seed, (uint64_t)obase, g.p_drop, ds);
 #pragma unroll
             for (int k = 0; k < V; ++k) {
-                const float xh = fmaf(v[k], rs[k], mr[k]);
                 float dd = d[k];
                 if (drop) dd *= ds[k];
-                if (g.act) dd *= hd_swish_grad(fmaf(xh, gam[k], bet[k]));
-                s1[k] += dd; s2[k] = fmaf(dd, xh, s2[k]);
+                if (g.act) dd *= hd_swish_grad(fmaf(v[k], A1[k], B1[k]));
+                s1[k] += dd; s2[k] = fmaf(dd, v[k], s2[k]);
             }
+          }
         }
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            int c = c0 + k, gi = c / cpg;
-            atomicAdd(&s_ch[c], s2[k]); atomicAdd(&s_ch[g.C + c], s1[k]);     // block-level first: one global atomic per channel per block
-            atomicAdd(&sg[gi][0], gam[k] * s1[k]); atomicAdd(&sg[gi][1], gam[k] * s2[k]);
+            const int c = c0 + k, gi = c / cpg;
+            const float gam = g.gamma[c];
+            const float sxh = s_rstd[gi] * (s2[k] - s_mean[gi] * s1[k]);       // sum(dy' * xhat)
+            atomicAdd(&s_ch[c], sxh); atomicAdd(&s_ch[g.C + c], s1[k]);        // block-level first: one global atomic per channel per block
+            atomicAdd(&sg[gi][0], gam * s1[k]); atomicAdd(&sg[gi][1], gam * sxh);
         }
     }
     __syncthreads();
@@ -294,13 +335,16 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g
     const int lane = threadIdx.x % lanes, sub = threadIdx.x / lanes;
     if (sub >= ppi) return;
     const int c0 = lane * V;
-    float gam[V], bet[V], rs[V], mr[V], ca[V], cb[V];
+    // z = v*A1 + B1 (pre-activation);  dx = A1*dy' - C1 - v*D1   with xhat = v*rstd + mr folded into C1 / D1
+    float A1[V], B1[V], C1[V], D1[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         const int c = c0 + k, gi = c / cpg;
-        gam[k] = g.gamma[c]; bet[k] = g.beta[c];
-        rs[k] = s_rstd[gi]; mr[k] = -s_mean[gi] * s_rstd[gi];
-        ca[k] = s_rstd[gi] * s_a[gi]; cb[k] = s_rstd[gi] * s_b[gi];
+        const float rs = s_rstd[gi], mr = -s_mean[gi] * rs;
+        A1[k] = rs * g.gamma[c];
+        B1[k] = fmaf(mr, g.gamma[c], g.beta[c]);
+        C1[k] = rs * (s_a[gi] + mr * s_b[gi]);
+        D1[k] = rs * rs * s_b[gi];
     }
     const bool first = c0 < x.C0;
     const int Cd = first ? x.C0 : x.C1, cd = first ? c0 : c0 - x.C0;
@@ -309,30 +353,42 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g
     const int64_t p0 = blockIdx.x * pix_per_block;
     const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
     const bool drop = g.p_drop > 0.f;
-#pragma unroll 2
-    for (int64_t pix = p0 + sub; pix < p1; pix += ppi) {
+    constexpr int U = 2;
+    for (int64_t pb = p0 + sub; pb < p1; pb += (int64_t)U * ppi) {
+      typename Vec<T>::raw xr[U], dr[U], ar[U], cr[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) if (pb + (int64_t)u * ppi < p1) {
+          const int64_t pix = pb + (int64_t)u * ppi;
+          xr[u] = raw_load(x.at(n, pix, g.HW, c0));
+          dr[u] = raw_load(dy + ((int64_t)n * g.HW + pix) * g.C + c0);
+          if (add) ar[u] = raw_load(add + ((int64_t)n * g.HW + pix) * g.C + c0);
+          if (acc) cr[u] = raw_load(acc + ((int64_t)n * g.HW + pix) * Cd + cd);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) if (pb + (int64_t)u * ppi < p1) {
+        const int64_t pix = pb + (int64_t)u * ppi;
         float v[V], d[V], r[V];
-        vec_load(x.at(n, pix, g.HW, c0), v);
+        unpack(xr[u], v);
         const int64_t obase = ((int64_t)n * g.HW + pix) * g.C + c0;
-        vec_load(dy + obase, d);
+        unpack(dr[u], d);
         float ds[V];
         if (drop) hd_dropout_vec<V>(g.seed, (uint64_t)obase, g.p_drop, ds);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            const float xh = fmaf(v[k], rs[k], mr[k]);
             float dd = d[k];
             if (drop) dd *= ds[k];
-            if (g.act) dd *= hd_swish_grad(fmaf(xh, gam[k], bet[k]));
-            r[k] = rs[k] * gam[k] * dd - ca[k] - xh * cb[k];
+            if (g.act) dd *= hd_swish_grad(fmaf(v[k], A1[k], B1[k]));
+            r[k] = fmaf(A1[k], dd, -fmaf(v[k], D1[k], C1[k]));
         }
-        if (add) { float t[V]; vec_load(add + obase, t);
+        if (add) { float t[V]; unpack(ar[u], t);
 #pragma unroll
             for (int k = 0; k < V; ++k) r[k] += t[k]; }
         const int64_t o = ((int64_t)n * g.HW + pix) * Cd + cd;
-        if (acc) { float t[V]; vec_load(acc + o, t);
+        if (acc) { float t[V]; unpack(cr[u], t);
 #pragma unroll
             for (int k = 0; k < V; ++k) r[k] += t[k]; }
         vec_store(dx + o, r);
+      }
     }
 }
 template <typename T>
@@ -373,11 +429,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* t, int N, int64_t 
         for (int k = 0; k < V; ++k) s[k] = 0.f;
         const int64_t p0 = blockIdx.x * pix_per_block;
         const int64_t p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
-    #pragma unroll 4
-        for (int64_t p = p0 + sub; p < p1; p += ppi) {
-            float v[V]; vec_load(t + ((int64_t)n * HW + p) * C + lane * V, v);
+            constexpr int U = 4;
+        for (int64_t p = p0 + sub; p < p1; p += (int64_t)U * ppi) {
+            typename Vec<T>::raw xr[U];
 #pragma unroll
-            for (int k = 0; k < V; ++k) s[k] += v[k];
+            for (int u = 0; u < U; ++u) if (p + (int64_t)u * ppi < p1) xr[u] = raw_load(t + ((int64_t)n * HW + p + (int64_t)u * ppi) * C + lane * V);
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (p + (int64_t)u * ppi < p1) {
+                float v[V]; unpack(xr[u], v);
+#pragma unroll
+                for (int k = 0; k < V; ++k) s[k] += v[k];
+            }
         }
 #pragma unroll
         for (int k = 0; k < V; ++k) atomicAdd(&s_col[lane * V + k], s[k]);
