@@ -212,18 +212,24 @@ int make_qkv_map(CUtensorMap* m, const void* qkv, int N, int S, int C3, int box_
 // Backward.  Two launches of one templated kernel, no atomics, deterministic:
 //   kDQ = true : the CTA owns 128 QUERY rows (X0 = Q, X1 = dO) and walks key tiles (Y0 = K, Y1 = V):   dQ  += dS K
 //   kDQ = false: the CTA owns 128 KEY rows   (X0 = K, X1 = V ) and walks query tiles (Y0 = Q, Y1 = dO): dK += dS^T Q, dV += P^T dO
-// Per ring tile (64 rows of Y):
-//   St  = X0 Y0^T   (scores, or their transpose)          SS MMA, fp32 in TMEM
-//   dPt = X1 Y1^T   (dO V^T, or its transpose)            SS MMA
-//   threads (lane = row of X): P = exp2(St * scale*log2e - lse*log2e), dS = P * (dPt - delta)   -> bf16 in TMEM (two buffers)
+// Per ring tile (64 rows of Y), score buffers b = tile & 1:
+//   St[b]  = X0 Y0^T   (scores, or their transpose)       SS MMA, fp32 in TMEM
+//   dPt[b] = X1 Y1^T   (dO V^T, or its transpose)         SS MMA
+//   8 element-wise warps (lane = row of X; two warps per lane quarter, 32 columns each):
+//       P = exp2(St * scale*log2e - lse*log2e), dS = P * (dPt - delta), written as bf16 IN PLACE over the first half of the
+//       warp's own St / dPt columns (so P / dS cost no extra tensor memory and the score buffers can be double-buffered)
 //   acc0 += dS Y0   [+ acc1 += P Y1]                      A from TMEM, B = the same Y tiles read MN-major
-// `stats` = [N][S][2] fp32 (lse*log2e, delta = rowsum(dO * O)), written by attn_stats_kernel.
+// The MMA thread issues St/dPt of tile j+1 BEFORE it waits for the element-wise result of tile j, so the tensor pipe always
+// has queued work and the mbarrier / TMEM-load latencies of the element-wise warps stay off the critical path.
+// `stats` = [N][S][2] fp32 (lse*log2e, delta = rowsum(dO * O)), written by attn_stats_kernel; in the key-row pass the 64
+// (lse, delta) pairs of a query tile travel with the tile through the shared-memory ring (one bulk copy).
 // ---------------------------------------------------------------------------------------------
 constexpr int kBwdStages = 3;
 constexpr int kXBytes = BM * D * 2;        // 32 KB per stationary operand
 constexpr int kYBytes = BN * D * 2;        // 16 KB per ring operand
-constexpr int kBwdStageBytes = 2 * kYBytes;
-constexpr uint32_t kColSt = 0, kColdPt = 64, kColPd = 128 /* 2 x (dS 32 | P 32) */, kColAcc0 = 256, kColAcc1 = 384;
+constexpr int kStatBytes = BN * 8;         // 64 x (lse*log2e, delta)
+constexpr int kBwdStageBytes = 2 * kYBytes + kStatBytes;
+constexpr uint32_t kColSt = 0 /* 2 x 64 */, kColdPt = 128 /* 2 x 64 */, kColAcc0 = 256, kColAcc1 = 384;
 
 struct AttnBwdParams {
     int N, S, tiles;
@@ -231,6 +237,11 @@ struct AttnBwdParams {
     const float2* stats;
     __nv_bfloat16* dqkv;
 };
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 // 8 element-wise warps: two per TMEM lane quarter, each owning 32 of the 64 score columns of a tile (a single warp per
 // scheduler cannot hide the MUFU / TMEM-load latencies of 128 values per thread and would leave the tensor pipe idle)
@@ -243,16 +254,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sX0 = smem;
     uint8_t* sX1 = smem + kXBytes;
-    uint8_t* sY = smem + 2 * kXBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kXBytes + kBwdStages * kBwdStageBytes);
+    uint8_t* sY = smem + 2 * kXBytes;                        // stages of (Y0 16 KB | Y1 16 KB)
+    uint8_t* sStat = sY + kBwdStages * 2 * kYBytes;          // stages of 512 B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + kBwdStages * kStatBytes);
     uint64_t* x_full = bars;                       // [1]
     uint64_t* y_full = bars + 1;                   // [3]
     uint64_t* y_empty = bars + 1 + kBwdStages;     // [3]
-    uint64_t* s_full = bars + 1 + 2 * kBwdStages;
-    uint64_t* s_empty = s_full + 1;
-    uint64_t* p_full = s_full + 2;
-    uint64_t* acc_done = s_full + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
+    uint64_t* s_full = bars + 1 + 2 * kBwdStages;  // [2]
+    uint64_t* p_full = s_full + 2;                 // [2]
+    uint64_t* acc_done = s_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = blockIdx.x * BM, n = blockIdx.y;
@@ -264,7 +275,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         tma_prefetch_desc(&mapQKV); tma_prefetch_desc(&mapDO);
         mbar_init(x_full, 1);
         for (int s = 0; s < kBwdStages; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-        mbar_init(s_full, 1); mbar_init(s_empty, 8); mbar_init(p_full, 8); mbar_init(acc_done, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); }
+        mbar_init(acc_done, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -286,10 +298,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
             int stage = 0; uint32_t phase = 0;
             for (int j = 0; j < T; ++j) {
                 mbar_wait(&y_empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&y_full[stage], kBwdStageBytes);
-                uint8_t* st = sY + stage * kBwdStageBytes;
+                mbar_arrive_expect_tx(&y_full[stage], kDQ ? 2 * kYBytes : kBwdStageBytes);
+                uint8_t* st = sY + stage * 2 * kYBytes;
                 for (int blk = 0; blk < 2; ++blk) tma_load_3d(st + blk * 8192, &mapQKV, &y_full[stage], cY0 + blk * 64, j * BN, n);
                 for (int blk = 0; blk < 2; ++blk) tma_load_3d(st + kYBytes + blk * 8192, mY1, &y_full[stage], cY1 + blk * 64, j * BN, n);
+                if (!kDQ) bulk_load_1d(sStat + stage * kStatBytes, p.stats + (long long)n * p.S + j * BN, kStatBytes, &y_full[stage]);
                 if (++stage == kBwdStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -299,45 +312,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
             const uint32_t idesc_acc = umma_idesc_bf16(BM, D, 0, 1);
             const uint32_t aX0 = smem_u32(sX0), aX1 = smem_u32(sX1);
             int ld_stage = 0; uint32_t ld_phase = 0;
-            auto issue_s = [&]() {
+            auto issue_s = [&](int j) {
                 mbar_wait(&y_full[ld_stage], ld_phase);
                 tc_fence_after();
-                const uint32_t aY0 = smem_u32(sY + ld_stage * kBwdStageBytes), aY1 = aY0 + kYBytes;
+                const uint32_t aY0 = smem_u32(sY + ld_stage * 2 * kYBytes), aY1 = aY0 + kYBytes;
+                const uint32_t b = (uint32_t)(j & 1) * 64;
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     const int blk = kk >> 2, sub = kk & 3;
-                    umma_bf16(tmem_base + kColSt, umma_smem_desc(aX0 + blk * (kXBytes / 2) + sub * 32, 16, 1024),
+                    umma_bf16(tmem_base + kColSt + b, umma_smem_desc(aX0 + blk * (kXBytes / 2) + sub * 32, 16, 1024),
                               umma_smem_desc(aY0 + blk * 8192 + sub * 32, 16, 1024), idesc_s, kk != 0);
                 }
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     const int blk = kk >> 2, sub = kk & 3;
-                    umma_bf16(tmem_base + kColdPt, umma_smem_desc(aX1 + blk * (kXBytes / 2) + sub * 32, 16, 1024),
+                    umma_bf16(tmem_base + kColdPt + b, umma_smem_desc(aX1 + blk * (kXBytes / 2) + sub * 32, 16, 1024),
                               umma_smem_desc(aY1 + blk * 8192 + sub * 32, 16, 1024), idesc_s, kk != 0);
                 }
-                umma_commit(s_full);
+                umma_commit(&s_full[j & 1]);
                 if (++ld_stage == kBwdStages) { ld_stage = 0; ld_phase ^= 1; }
             };
             mbar_wait(x_full, 0);
-            issue_s();
+            issue_s(0);
             int stage = 0;
             for (int j = 0; j < T; ++j) {
-                if (j + 1 < T) {
-                    mbar_wait(s_empty, j & 1);
-                    tc_fence_after();
-                    issue_s();
-                }
-                mbar_wait(p_full, j & 1);
+                // scores of tile j+1 go to the other buffer.  Its last readers were the accumulation MMAs of tile j-1, issued
+                // earlier by this thread (the tensor pipe executes in issue order), and the element-wise loads of tile j-1,
+                // which completed before p_full of tile j-1 — already waited for.
+                if (j + 1 < T) issue_s(j + 1);
+                mbar_wait(&p_full[j & 1], (j >> 1) & 1);
                 tc_fence_after();
-                const uint32_t aY0 = smem_u32(sY + stage * kBwdStageBytes), aY1 = aY0 + kYBytes;
-                const uint32_t tPd = tmem_base + kColPd + (j & 1) * 64;
+                const uint32_t aY0 = smem_u32(sY + stage * 2 * kYBytes), aY1 = aY0 + kYBytes;
+                const uint32_t b = (uint32_t)(j & 1) * 64;
+                // P / dS sit in the first 16 columns of each warp's 32-column range: K steps 0,1 -> +0,+8 ; 2,3 -> +32,+40
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16_ts(tmem_base + kColAcc0, tPd + kk * 8, umma_smem_desc(aY0 + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0);
+                    umma_bf16_ts(tmem_base + kColAcc0, tmem_base + kColdPt + b + (kk >> 1) * 32 + (kk & 1) * 8,
+                                 umma_smem_desc(aY0 + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0);
                 if (!kDQ) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16_ts(tmem_base + kColAcc1, tPd + 32 + kk * 8, umma_smem_desc(aY1 + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0);
+                        umma_bf16_ts(tmem_base + kColAcc1, tmem_base + kColSt + b + (kk >> 1) * 32 + (kk & 1) * 8,
+                                     umma_smem_desc(aY1 + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0);
                 }
                 umma_commit(&y_empty[stage]);
                 if (++stage == kBwdStages) stage = 0;
@@ -350,26 +366,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const float sl2 = p.scale_log2;
-        const float2* stats_n = p.stats + (long long)n * p.S;
         float2 my = make_float2(0.f, 0.f);
-        if (kDQ) my = __ldg(stats_n + r0 + row);
+        if (kDQ) my = __ldg(p.stats + (long long)n * p.S + r0 + row);
+        int stage = 0; uint32_t y_phase = 0;
         for (int j = 0; j < T; ++j) {
-            mbar_wait(s_full, j & 1);
+            if (!kDQ) mbar_wait(&y_full[stage], y_phase);    // the tile's (lse, delta) pairs were bulk-copied with it
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
-            const uint32_t tPd = lane_base + kColPd + (j & 1) * 64;
+            const uint32_t tS = lane_base + kColSt + (uint32_t)(j & 1) * 64 + h * 32;
+            const uint32_t tD = lane_base + kColdPt + (uint32_t)(j & 1) * 64 + h * 32;
             uint32_t sv[32], dv[32];
-            tmem_ld32(lane_base + kColSt + h * 32, sv);
-            tmem_ld32(lane_base + kColdPt + h * 32, dv);
+            tmem_ld32(tS, sv);
+            tmem_ld32(tD, dv);
             tmem_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty);     // this warp's share of the score columns is in registers
+            const float4* st4 = reinterpret_cast<const float4*>(sStat + stage * kStatBytes) + h * 16;   // s_full implies y_full
             uint32_t pp[16], ds[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 float2 s0 = my, s1 = my;
                 if (!kDQ) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(stats_n + j * BN + h * 32 + 2 * i));
+                    const float4 q = st4[i];         // same address in every lane: a shared-memory broadcast
                     s0 = make_float2(q.x, q.y); s1 = make_float2(q.z, q.w);
                 }
                 const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * i]), sl2, -s0.x));
@@ -379,12 +395,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
                 pp[i] = pack_bf16x2(p0, p1);
                 ds[i] = pack_bf16x2(d0, d1);
             }
-            tmem_st16(tPd + h * 16, ds);
-            if (!kDQ) tmem_st16(tPd + 32 + h * 16, pp);
+            tmem_st16(tD, ds);
+            if (!kDQ) tmem_st16(tS, pp);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
+            if (lane == 0) mbar_arrive(&p_full[j & 1]);
+            if (++stage == kBwdStages) { stage = 0; y_phase ^= 1; }
         }
         mbar_wait(acc_done, 0);
         tc_fence_after();
@@ -475,7 +492,7 @@ extern "C" int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout
     p.scale = 1.f / sqrtf((float)C);
     p.scale_log2 = 1.4426950408889634f * p.scale;
     p.stats = (const float2*)stats; p.dqkv = (__nv_bfloat16*)dqkv;
-    const size_t smem = 2 * kXBytes + kBwdStages * kBwdStageBytes + 1024 + 16 * 8;
+    const size_t smem = 2 * kXBytes + kBwdStages * kBwdStageBytes + 1024 + 20 * 8;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
