@@ -235,6 +235,44 @@ def run_ours(args):
                     "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak, "traffic": None,
                     "peak_source": peaks["source"] + (" sustained bf16 (kernel timed inside a long step)" if tensor else " copy bandwidth"),
                     "share_of_timed_kernels": f["ms"] / tot}
+    # ---- CFG sampling (the second half of BASELINE.json's metric): configs[3] shape, a bounded number of the 1000 steps ----
+    sampling = None
+    if args.sample_steps > 0:
+        del trainer, opt, dev_pool
+        net._state = None
+        del net
+        torch.cuda.empty_cache()
+        from hdiff_b200.DiffusionFreeGuidence.ModelCondition import UNet as CondUNet
+        from hdiff_b200.DiffusionFreeGuidence.DiffusionCondition import GaussianDiffusionSampler
+        torch.manual_seed(0)
+        cfg = dict(CFG2); cfg["dropout"] = 0.0
+        snet = CondUNet(num_labels=10, **cfg).to(dev)
+        snet.eval()
+        sampler = GaussianDiffusionSampler(snet, BETA_1, BETA_T, CFG2["T"], w=1.8).to(dev)
+        Bs = args.sample_batch
+        torch.manual_seed(2000 + rank)
+        x = torch.randn(Bs, 3, res, res, device=dev)
+        labels = (torch.arange(Bs, device=dev) + rank * Bs) % 10 + 1
+        step = torch.full((1,), CFG2["T"] - 1, dtype=torch.int32, device=dev)
+        nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        sampler.run_steps(x, labels, step, nan_flag, 3)                     # warm-up (includes graph capture cost once)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l1 = ops.launches
+        s0.record()
+        sampler.run_steps(x, labels, step, nan_flag, args.sample_steps)
+        s1.record()
+        barrier()
+        sms = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        per_step = float(sms.item()) / args.sample_steps
+        sampling = {"metric": "cfg_sampling_images_per_sec_256", "value": world * Bs / (per_step * 1e-3 * CFG2["T"]), "unit": UNIT,
+                    "ms_per_sampler_step": per_step, "sampler_steps_timed": args.sample_steps,
+                    "note": f"{args.sample_steps} of the {CFG2['T']} ancestral steps timed (each = one 2B-batch conditional+null UNet forward "
+                            "+ fused CFG/posterior update), extrapolated to the full chain; includes one CUDA-graph capture",
+                    "batch_per_gpu": Bs, "global_batch": world * Bs, "guidance_w": 1.8, "cuda_graph": bool(sampler.use_cuda_graph),
+                    "nan_flag": int(nan_flag.item())}
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     if rank != 0:
@@ -252,7 +290,7 @@ def run_ours(args):
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * B * 3 * res * res * 4, "d2h_bytes_per_step": world * 4,
                    "ms_per_step": ms_e2e / args.steps},
            "gpu_launches": launches, "tcgen05_launches_total": ops.tc_launches, "loss": loss_val,
-           "roofline": roof, "kernel_families": fam_out, "clocks": clk}
+           "roofline": roof, "kernel_families": fam_out, "clocks": clk, "sampling": sampling}
     if world == 1 and not args.no_cpu_baseline:
         v, sec, threads = cpu_reference_steps(args.cpu_steps, 1, res, args.ref_batch)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -276,6 +314,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=1, help="batch of the CPU reference sample")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample-steps", type=int, default=20, help="ancestral sampler steps timed after the training measurement (0: skip)")
+    ap.add_argument("--sample-batch", type=int, default=8, help="per-GPU sampling batch (configs[3]: 64 images over 8 GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,7 +14,10 @@ int hd_make_act_tmap(CUtensorMap* m, const void* base, int C, int P, int N, int 
 
 namespace {
 
-constexpr int kThreads = 192;
+// warp 0 + warps 6..: TMA producers (a stage is up to 12 tensor copies; one issuing thread is the bottleneck, so the
+// copies of a stage are dealt round-robin to kProducers threads), warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kProducers = 4;
+constexpr int kThreads = 192 + 32 * (kProducers - 1);
 constexpr int kBlkBytes = 64 * 128;    // one [64 pixels][64 channels] bf16 box
 constexpr int kMaxStages = 8;
 
@@ -52,7 +55,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapX0); tma_prefetch_desc(&mapX1); tma_prefetch_desc(&mapDY);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], kProducers); mbar_init(&empty[s], 1); }
         mbar_init(tfull, 1);
         fence_barrier_init();
     }
@@ -62,9 +65,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 0 || warp >= 6) {
+        const int prod = warp == 0 ? 0 : warp - 5;
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
+            // bytes this producer brings per stage: copies b (0 .. 2G+nb-1) with b % kProducers == prod
+            int my_loads = 0;
+            for (int b = prod; b < 2 * p.G + p.nb; b += kProducers) ++my_loads;
             // the (tap, parity, chunk) coordinates of this CTA's operand blocks do not depend on the pixel tile: decode
             // them once (the divisions below used to sit in the per-tile loop of this single thread)
             constexpr int kMaxBlk = 8;
@@ -84,18 +91,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
             for (int t = t_begin; t < t_end; ++t) {
                 const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
                 mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                mbar_arrive_expect_tx(&full[stage], (uint32_t)(my_loads * kBlkBytes));
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
 #pragma unroll
                 for (int b = 0; b < kMaxBlk; ++b) {
-                    if (b < 2 * p.G) {
+                    if (b < 2 * p.G && (b % kProducers) == prod) {
                         if (a_c[b] < p.nchunk0) tma_load_5d(sa + b * kBlkBytes, &mapX0, &full[stage], a_c[b] * 64, x0 + a_dx[b], a_py[b], y0 + a_dy[b], n);
                         else tma_load_5d(sa + b * kBlkBytes, &mapX1, &full[stage], (a_c[b] - p.nchunk0) * 64, x0 + a_dx[b], a_py[b], y0 + a_dy[b], n);
                     }
                 }
                 int cc = dy_c0, py = dy_py0;
                 for (int b = 0; b < p.nb; ++b) {
-                    tma_load_5d(sa + a_bytes + b * kBlkBytes, &mapDY, &full[stage], cc * 64, x0, py, y0, n);
+                    if (((2 * p.G + b) % kProducers) == prod)
+                        tma_load_5d(sa + a_bytes + b * kBlkBytes, &mapDY, &full[stage], cc * 64, x0, py, y0, n);
                     if (++cc == p.nch_dy) { cc = 0; ++py; }
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
