@@ -270,7 +270,8 @@ def run_ours(args):
         sampling = {"metric": "cfg_sampling_images_per_sec_256", "value": world * Bs / (per_step * 1e-3 * CFG2["T"]), "unit": UNIT,
                     "ms_per_sampler_step": per_step, "sampler_steps_timed": args.sample_steps,
                     "note": f"{args.sample_steps} of the {CFG2['T']} ancestral steps timed (each = one 2B-batch conditional+null UNet forward "
-                            "+ fused CFG/posterior update), extrapolated to the full chain; includes one CUDA-graph capture",
+                            "+ fused CFG/posterior update) as replays of the step's CUDA graph (captured once during warm-up, as it is once per 1000-step "
+                            "chain), extrapolated to the full chain",
                     "batch_per_gpu": Bs, "global_batch": world * Bs, "guidance_w": 1.8, "cuda_graph": bool(sampler.use_cuda_graph),
                     "nan_flag": int(nan_flag.item())}
     value = world * B * args.steps / (ms * 1e-3)

@@ -46,6 +46,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint64_t* tfull = bars + 2 * kMaxStages;     // [2]
     uint64_t* tempty = bars + 2 * kMaxStages + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    float* addend = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);     // [2][256]: bias + embedding row of a tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -127,10 +128,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const int ty_i = r % p.tiles_y; const int n = r / p.tiles_y;
             const int y = ty_i * p.TH + ty, x = tx_i * p.TW + tx;
             const bool valid = y < p.H;
+            // per-channel addend (bias + this image's embedding row) staged once per tile while the MMAs still run; the
+            // element loop then reads it as shared-memory broadcasts instead of 32 dependent global loads per chunk
+            float* add_t = addend + acc * 256;
+            {
+                const float* emb_row = p.emb ? p.emb + (long long)n * p.emb_stride : nullptr;
+                for (int c = row; c < p.NT; c += 128) {
+                    const int j = n_tile * p.NT + c;
+                    float a = p.bias ? __ldg(p.bias + j) : 0.f;
+                    if (emb_row) a += __ldg(emb_row + j);
+                    add_t[c] = a;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+            }
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
-            const float* emb_row = p.emb ? p.emb + (long long)n * p.emb_stride : nullptr;
             if (p.out_nchw) {
                 if (n_tile == 0) {
                     uint32_t v[16];
@@ -140,8 +153,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             if (i < p.nchw_c) {
-                                float f = __uint_as_float(v[i]);
-                                if (p.bias) f += __ldg(p.bias + i);
+                                const float f = __uint_as_float(v[i]) + add_t[i];
                                 p.out_nchw[(((long long)n * p.nchw_c + i) * p.H + y) * p.W + x] = f;
                             }
                         }
@@ -162,15 +174,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         off = (((long long)n * (2 * p.H) + (2 * y + (q >> 1))) * (2 * p.W) + (2 * x + (q & 1))) * p.Cout + cph;
                     }
                     float f[16];
+                    const float4* a4 = reinterpret_cast<const float4*>(add_t + c);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-                    if (p.bias) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + j + i);
-                    }
-                    if (emb_row) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] += __ldg(emb_row + j + i);
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a = a4[i];
+                        f[4 * i] = __uint_as_float(v[4 * i]) + a.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + a.y;
+                        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + a.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + a.w;
                     }
                     if (p.res) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
@@ -307,7 +316,7 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
         uint32_t box[2] = {64, (uint32_t)p.NT};
         rc = hd_make_tmap_bf16(&mB, w, 2, dims, str, box); if (rc) return rc;
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 4) * 8 + 16;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 2 * 256 * 4;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(conv_tc_kernel)"); return HD_ERR_CUDA; }
