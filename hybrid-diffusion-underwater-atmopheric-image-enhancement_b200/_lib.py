@@ -27,6 +27,7 @@ PROTOTYPES = {
     "hd_gn_apply": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P],
     "hd_gn_bwd_reduce": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P],
     "hd_gn_bwd_apply": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P, P, P, P],
+    "hd_gn_bwd_fused": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P, P, P, P, P, P, P],
     "hd_colsum": [I, P, I, I, L, I, P, L, P, P],
     "hd_q_sample": [P, P, P, P, P, P, I, L, P],
     "hd_mse_fwd": [P, P, P, L, P],
@@ -37,6 +38,7 @@ PROTOTYPES = {
     "hd_adamw_flat": [P, P, P, P, L, P, F, F, F, F, F, F, I, P],
     "hd_conv_tc": [P, I, P, I, I, P, P, P, L, P, P, I, I, I, I, I, I, I, P],
     "hd_pad_nchw": [P, I, P, I, L, P],
+    "hd_probe_shift": [P, P, P, I, I, P],
     "hd_conv_tc_supported": [I, I, I, I, I, I, I, I],
     "hd_wgrad_tc": [P, I, P, I, I, P, I, I, P, P, L, I, I, I, I, P],
     "hd_wgrad_tc_supported": [I, I, I, I, I, I, I, I],

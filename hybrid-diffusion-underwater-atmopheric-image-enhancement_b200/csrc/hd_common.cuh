@@ -49,6 +49,16 @@ template <> __device__ __forceinline__ void hd_st<__nv_bfloat16>(__nv_bfloat16* 
 
 // MUFU.EX2 + MUFU.RCP (a few ulp): an IEEE division here costs more issue slots than the rest of a GroupNorm element
 __device__ __forceinline__ float hd_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// single-MUFU sigmoid (tanh.approx, |error| ~ 2.5e-4): used by the bf16 kernels only, where it is below the storage rounding;
+// it halves the transcendental-pipe work of the GroupNorm kernels, which are issue-bound rather than bandwidth-bound
+__device__ __forceinline__ float hd_sigmoid_fast(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
+template <bool kFast> __device__ __forceinline__ float hd_sigmoid_t(float x) { return kFast ? hd_sigmoid_fast(x) : hd_sigmoid(x); }
+template <bool kFast> __device__ __forceinline__ float hd_swish_t(float x) { return x * hd_sigmoid_t<kFast>(x); }
+template <bool kFast> __device__ __forceinline__ float hd_swish_grad_t(float x) { float s = hd_sigmoid_t<kFast>(x); return s * fmaf(x, 1.f - s, 1.f); }
 __device__ __forceinline__ float hd_swish(float x) { return x * hd_sigmoid(x); }
 __device__ __forceinline__ float hd_swish_grad(float x) { float s = hd_sigmoid(x); return s * (1.f + x * (1.f - s)); }
 

@@ -9,8 +9,8 @@
 #include "hd_common.cuh"
 
 template <typename T> struct Vec;
-template <> struct Vec<float> { static constexpr int N = 4; using raw = float4; };
-template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; using raw = uint4; };
+template <> struct Vec<float> { static constexpr int N = 4; using raw = float4; static constexpr bool fast = false; };
+template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; using raw = uint4; static constexpr bool fast = true; };
 
 template <typename T> __device__ __forceinline__ void vec_load(const T* p, float* v);
 template <> __device__ __forceinline__ void vec_load<float>(const float* p, float* v) {
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> x, GnParams g, in
 #pragma unroll
                 for (int k = 0; k < V; ++k) {
                     float z = fmaf(v[k], a[k], b[k]);
-                    if (g.act) z = hd_swish(z);
+                    if (g.act) z = hd_swish(z);      // forward keeps the EX2 + RCP sigmoid: its error is absolute, not relative
                     if (drop) z *= ds[k];
                     v[k] = z;
                 }
@@ -223,12 +223,10 @@ extern "C" int hd_gn_apply(int dtype, const void* in0, int C0, const void* in1, 
 // dy' = dy * drop * act'(z).  Per channel: dgamma += sum dy' xhat, dbeta += sum dy'.
 // Per (n, group): gsums = (sum gamma dy', sum gamma dy' xhat).
 template <typename T>
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams g, const T* dy, int64_t pix_per_block,
-                                                            double* gsums, float* dgamma, float* dbeta) {
+__device__ __forceinline__ void gn_bwd_reduce_body(const Src2<T>& x, const GnParams& g, const T* dy, int64_t pix_per_block,
+                                                   double* gsums, float* dgamma, float* dbeta, int n, int blk,
+                                                   float* s_mean, float* s_rstd, float (*sg)[2], float* s_ch) {
     constexpr int V = Vec<T>::N;
-    __shared__ float s_mean[64], s_rstd[64], sg[64][2];
-    extern __shared__ float s_ch[];               // [2][C]: per-channel (dgamma, dbeta) partials of this block
-    const int n = blockIdx.y;
     gn_load_stats(g, n, s_mean, s_rstd);
     for (int i = threadIdx.x; i < g.G; i += blockDim.x) { sg[i][0] = 0.f; sg[i][1] = 0.f; }
     for (int i = threadIdx.x; i < 2 * g.C; i += blockDim.x) s_ch[i] = 0.f;
@@ -249,7 +247,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams 
             s1[k] = 0.f; s2[k] = 0.f;
         }
         const bool drop = g.p_drop > 0.f;
-        const int64_t p0 = blockIdx.x * pix_per_block;
+        const int64_t p0 = blk * pix_per_block;
         const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
         constexpr int U = 4;
         for (int64_t pb = p0 + sub; pb < p1; pb += (int64_t)U * ppi) {
@@ -272,7 +270,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams 
             for (int k = 0; k < V; ++k) {
                 float dd = d[k];
                 if (drop) dd *= ds[k];
-                if (g.act) dd *= hd_swish_grad(fmaf(v[k], A1[k], B1[k]));
+                if (g.act) dd *= hd_swish_grad_t<Vec<T>::fast>(fmaf(v[k], A1[k], B1[k]));
                 s1[k] += dd; s2[k] = fmaf(dd, v[k], s2[k]);
             }
           }
@@ -292,6 +290,14 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams 
         atomicAdd(gsums + ((int64_t)n * g.G + i) * 2, (double)sg[i][0]);
         atomicAdd(gsums + ((int64_t)n * g.G + i) * 2 + 1, (double)sg[i][1]);
     }
+    __syncthreads();                              // the shared partials may be reused by the caller's next work item
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams g, const T* dy, int64_t pix_per_block,
+                                                            double* gsums, float* dgamma, float* dbeta) {
+    __shared__ float s_mean[64], s_rstd[64], sg[64][2];
+    extern __shared__ float s_ch[];               // [2][C]: per-channel (dgamma, dbeta) partials of this block
+    gn_bwd_reduce_body<T>(x, g, dy, pix_per_block, gsums, dgamma, dbeta, blockIdx.y, blockIdx.x, s_mean, s_rstd, sg, s_ch);
 }
 template <typename T>
 static int gn_bwd_reduce_t(const void* in0, int C0, const void* in1, int C1, GnParams g, const void* dy, double* gsums,
@@ -318,22 +324,21 @@ extern "C" int hd_gn_bwd_reduce(int dtype, const void* in0, int C0, const void* 
 // dx = rstd * (gamma dy' - A/m - xhat B/m) + add + acc ; written to two destination tensors.
 // thread <-> fixed channel vector, per-channel constants hoisted out of the pixel loop.
 template <typename T>
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g, const T* dy, const double* gsums, const T* add,
-                                                           const T* acc0, const T* acc1, T* dx0, T* dx1, int64_t pix_per_block) {
+__device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& x, const GnParams& g, const T* dy, const double* gsums, const T* add,
+                                                  const T* acc0, const T* acc1, T* dx0, T* dx1, int64_t pix_per_block, int n, int blk,
+                                                  float* s_mean, float* s_rstd, float* s_a, float* s_b) {
     constexpr int V = Vec<T>::N;
-    __shared__ float s_mean[64], s_rstd[64], s_a[64], s_b[64];
-    const int n = blockIdx.y;
     gn_load_stats(g, n, s_mean, s_rstd);
     const double m = (double)(g.C / g.G) * (double)g.HW;
     for (int i = threadIdx.x; i < g.G; i += blockDim.x) {
-        s_a[i] = (float)(gsums[((int64_t)n * g.G + i) * 2] / m);
-        s_b[i] = (float)(gsums[((int64_t)n * g.G + i) * 2 + 1] / m);
+        s_a[i] = (float)(__ldcg(gsums + ((int64_t)n * g.G + i) * 2) / m);        // L2: written by atomics (maybe of this launch)
+        s_b[i] = (float)(__ldcg(gsums + ((int64_t)n * g.G + i) * 2 + 1) / m);
     }
     __syncthreads();
     const int lanes = g.C / V, cpg = g.C / g.G;
     const int ppi = blockDim.x / lanes;
     const int lane = threadIdx.x % lanes, sub = threadIdx.x / lanes;
-    if (sub >= ppi) return;
+    if (sub < ppi) {
     const int c0 = lane * V;
     // z = v*A1 + B1 (pre-activation);  dx = A1*dy' - C1 - v*D1   with xhat = v*rstd + mr folded into C1 / D1
     float A1[V], B1[V], C1[V], D1[V];
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g
     const int Cd = first ? x.C0 : x.C1, cd = first ? c0 : c0 - x.C0;
     const T* acc = first ? acc0 : acc1;
     T* dx = first ? dx0 : dx1;
-    const int64_t p0 = blockIdx.x * pix_per_block;
+    const int64_t p0 = blk * pix_per_block;
     const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
     const bool drop = g.p_drop > 0.f;
     constexpr int U = 2;
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g
         for (int k = 0; k < V; ++k) {
             float dd = d[k];
             if (drop) dd *= ds[k];
-            if (g.act) dd *= hd_swish_grad(fmaf(v[k], A1[k], B1[k]));
+            if (g.act) dd *= hd_swish_grad_t<Vec<T>::fast>(fmaf(v[k], A1[k], B1[k]));
             r[k] = fmaf(A1[k], dd, -fmaf(v[k], D1[k], C1[k]));
         }
         if (add) { float t[V]; unpack(ar[u], t);
@@ -390,6 +395,85 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g
         vec_store(dx + o, r);
       }
     }
+    }
+    __syncthreads();                              // the shared statistics may be reused by the caller's next work item
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g, const T* dy, const double* gsums, const T* add,
+                                                           const T* acc0, const T* acc1, T* dx0, T* dx1, int64_t pix_per_block) {
+    __shared__ float s_mean[64], s_rstd[64], s_a[64], s_b[64];
+    gn_bwd_apply_body<T>(x, g, dy, gsums, add, acc0, acc1, dx0, dx1, pix_per_block, blockIdx.y, blockIdx.x, s_mean, s_rstd, s_a, s_b);
+}
+
+// ------------------------------- backward, both passes in one launch ------------------------
+// The reduction and the apply pass both read x and dy.  Walking the batch in groups of images whose x + dy fit the L2
+// (all CTAs reduce a group, meet at a grid barrier, then apply to the same group) turns the second read into L2 hits:
+// HBM traffic drops from 5 tensor passes to 3.  Cooperative launch (all CTAs co-resident), one barrier per group.
+__device__ __forceinline__ void hd_grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
+    }
+    __syncthreads();
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_fused_kernel(Src2<T> x, GnParams g, const T* dy, double* gsums, float* dgamma, float* dbeta,
+                                                           const T* add, const T* acc0, const T* acc1, T* dx0, T* dx1,
+                                                           int64_t pix_per_block, int chunks, int group, unsigned* counter) {
+    __shared__ float s_mean[64], s_rstd[64], sg[64][2], s_a[64], s_b[64];
+    extern __shared__ float s_ch[];
+    unsigned round = 0;
+    for (int n0 = 0; n0 < g.N; n0 += group) {
+        const int nimg = g.N - n0 < group ? g.N - n0 : group;
+        for (int vb = blockIdx.x; vb < nimg * chunks; vb += gridDim.x)
+            gn_bwd_reduce_body<T>(x, g, dy, pix_per_block, gsums, dgamma, dbeta, n0 + vb / chunks, vb % chunks, s_mean, s_rstd, sg, s_ch);
+        hd_grid_barrier(counter, ++round * gridDim.x);
+        for (int vb = blockIdx.x; vb < nimg * chunks; vb += gridDim.x)
+            gn_bwd_apply_body<T>(x, g, dy, gsums, add, acc0, acc1, dx0, dx1, pix_per_block, n0 + vb / chunks, vb % chunks, s_mean, s_rstd, s_a, s_b);
+    }
+}
+template <typename T>
+static int gn_bwd_fused_t(const void* in0, int C0, const void* in1, int C1, GnParams g, const void* dy, double* gsums, float* dgamma,
+                          float* dbeta, const void* add, const void* acc0, const void* acc1, void* dx0, void* dx1, unsigned* counter,
+                          cudaStream_t st) {
+    int rc = gn_check<T>(C0, C1, g.G); if (rc) return rc;
+    if (cudaMemsetAsync(gsums, 0, sizeof(double) * 2 * (size_t)g.N * g.G, st) != cudaSuccess) return HD_ERR_CUDA;
+    if (cudaMemsetAsync(counter, 0, sizeof(unsigned), st) != cudaSuccess) return HD_ERR_CUDA;
+    const size_t dsm = 2 * g.C * sizeof(float);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_bwd_fused_kernel<T>, 256, dsm) != cudaSuccess || per_sm < 1) {
+        hd_set_error("gn_bwd_fused: occupancy query failed"); return HD_ERR_CUDA;
+    }
+    const int grid = per_sm * hd_num_sms();
+    // images per group: x + dy of the group within ~48 MB of the 126 MB L2
+    const int64_t per_img = 2 * g.HW * g.C * (int64_t)sizeof(T);
+    int group = (int)((48ll << 20) / per_img); if (group < 1) group = 1; if (group > g.N) group = g.N;
+    const int ppi = 256 / (g.C / Vec<T>::N);
+    int chunks = grid / group; if (chunks < 1) chunks = 1;
+    int64_t ppb = (g.HW + chunks - 1) / chunks; ppb = (ppb + ppi - 1) / ppi * ppi;
+    chunks = (int)((g.HW + ppb - 1) / ppb);
+    Src2<T> x{(const T*)in0, (const T*)in1, C0, C1};
+    const T* dyp = (const T*)dy; const T* addp = (const T*)add; const T* a0 = (const T*)acc0; const T* a1 = (const T*)acc1;
+    T* d0 = (T*)dx0; T* d1 = (T*)dx1;
+    void* args[] = {&x, &g, &dyp, &gsums, &dgamma, &dbeta, &addp, &a0, &a1, &d0, &d1, &ppb, &chunks, &group, &counter};
+    if (cudaLaunchCooperativeKernel((const void*)gn_bwd_fused_kernel<T>, dim3(grid), dim3(256), args, dsm, st) != cudaSuccess) {
+        hd_set_error(cudaGetErrorString(cudaGetLastError())); return HD_ERR_CUDA;
+    }
+    return HD_OK;
+}
+// gsums: [N][G][2] fp64 scratch, counter: one zero-initialisable unsigned of scratch (grid barrier)
+extern "C" int hd_gn_bwd_fused(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G,
+                               const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
+                               uint64_t seed, const void* dy, double* gsums, float* dgamma, float* dbeta, const void* add,
+                               const void* acc0, const void* acc1, void* dx0, void* dx1, unsigned* counter, cudaStream_t stream) {
+    HD_REQUIRE(in0 && sums && gamma && beta && dy && gsums && dgamma && dbeta && dx0 && counter && (C1 == 0 || (in1 && dx1)));
+    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
+    if (dtype == HD_F32) return gn_bwd_fused_t<float>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, add, acc0, acc1, dx0, dx1, counter, stream);
+    if (dtype == HD_BF16) return gn_bwd_fused_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, add, acc0, acc1, dx0, dx1, counter, stream);
+    return HD_ERR_ARG;
 }
 template <typename T>
 static int gn_bwd_apply_t(const void* in0, int C0, const void* in1, int C1, GnParams g, const void* dy, const double* gsums,

@@ -35,6 +35,8 @@ class CudaOps:
         self.use_tc = True          # tcgen05 kernels where the shape is covered
         self.launches = 0           # kernels launched through this object (bench.py reports it)
         self.tc_launches = 0
+        self.gn_fused = __import__("os").environ.get("HDIFF_GN_FUSED", "0") != "0"   # one cooperative launch per GroupNorm backward (measured slower: see DESIGN.md)
+        self._gn_counter = None
         self.prof = None            # bench.py: dict family -> [(start_event, end_event, work)], CUDA events on the launch stream
 
     # ---- per-launch device timing for bench.py's roofline (off unless `prof` is a dict) ----
@@ -165,13 +167,17 @@ class CudaOps:
         C0, C1 = x0.shape[-1], 0 if x1 is None else x1.shape[-1]
         dt = _DT[x0.dtype]
         e0 = self._t0()
-        _lib.check(self.lib.hd_gn_bwd_reduce(dt, _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _p(gamma), _p(beta), eps,
-                                             int(act), float(p_drop), int(seed), _p(dy), _p(gsums), _p(dgamma), _p(dbeta),
-                                             _stream()), "hd_gn_bwd_reduce")
-        _lib.check(self.lib.hd_gn_bwd_apply(dt, _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _p(gamma), _p(beta), eps,
-                                            int(act), float(p_drop), int(seed), _p(dy), _p(gsums), _p(add), _p(acc0), _p(acc1),
-                                            _p(dx0), _p(dx1), _stream()), "hd_gn_bwd_apply")
-        self.launches += 2
+        a = (dt, _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _p(gamma), _p(beta), eps, int(act), float(p_drop), int(seed), _p(dy))
+        if self.gn_fused:
+            if self._gn_counter is None or self._gn_counter.device != x0.device:
+                self._gn_counter = torch.zeros(1, dtype=torch.int32, device=x0.device)
+            _lib.check(self.lib.hd_gn_bwd_fused(*a, _p(gsums), _p(dgamma), _p(dbeta), _p(add), _p(acc0), _p(acc1), _p(dx0), _p(dx1),
+                                                _p(self._gn_counter), _stream()), "hd_gn_bwd_fused")
+            self.launches += 1
+        else:
+            _lib.check(self.lib.hd_gn_bwd_reduce(*a, _p(gsums), _p(dgamma), _p(dbeta), _stream()), "hd_gn_bwd_reduce")
+            _lib.check(self.lib.hd_gn_bwd_apply(*a, _p(gsums), _p(add), _p(acc0), _p(acc1), _p(dx0), _p(dx1), _stream()), "hd_gn_bwd_apply")
+            self.launches += 2
         nt = 5 + (add is not None) + (acc0 is not None)       # x, dy twice; dx once; optional addends
         self._t1(e0, "gn_bwd", float(nt * N * HW * (C0 + C1) * x0.element_size()))
 

@@ -83,6 +83,12 @@ int hd_gn_bwd_apply(int dtype, const void* in0, int C0, const void* in1, int C1,
                     const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
                     uint64_t seed, const void* dy, const double* gsums, const void* add, const void* acc0,
                     const void* acc1, void* dx0, void* dx1, hd_stream_t stream);
+/* both passes in one cooperative launch, the batch walked in L2-sized image groups (3 HBM tensor passes instead of 5);
+ * gsums = [N][G][2] fp64 scratch, counter = 4 bytes of scratch for the grid barrier */
+int hd_gn_bwd_fused(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G,
+                    const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
+                    uint64_t seed, const void* dy, double* gsums, float* dgamma, float* dbeta, const void* add,
+                    const void* acc0, const void* acc1, void* dx0, void* dx1, unsigned* counter, hd_stream_t stream);
 /* bias / embedding-add gradients: per-sample and total column sums (both accumulate) */
 int hd_colsum(int dtype, const void* t, int nchw_f32, int N, int64_t HW, int C, float* per_n, int64_t ld_per_n,
               float* total, hd_stream_t stream);
@@ -113,6 +119,9 @@ int hd_mse_bwd(const float* pred, const float* noise, const float* g, float* dpr
 int hd_sampler_step(float* x, const float* eps_c, const float* eps_u, const float* z, float w1, float w, const float* coef,
                     const int* step_ptr, int last_step_clip, int* nan_flag, int64_t n, hd_stream_t stream);
 int hd_add_int(int* p, int delta, hd_stream_t stream);
+
+/* ---- hardware probe (scripts/probe_shift.py): tcgen05 A operand starting at an arbitrary 128-byte row of a swizzled box ---- */
+int hd_probe_shift(const void* x, const void* w, float* out, int shift, int mode, hd_stream_t stream);
 
 /* ---- clip_grad_norm_ + AdamW on the flat buffers (TrainCondition.py:39,61-63) ---- */
 int hd_sqnorm(const float* g, int64_t n, double* out, hd_stream_t stream);

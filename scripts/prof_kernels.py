@@ -51,8 +51,8 @@ if what in ("conv", "wgrad", "all"):
             timeit(f"wgrad{k}x{k} N{N} {H}x{W} {C0}+{C1}->{Cout}", lambda: ops.wgrad(x0, x1, 1, dy, 1, dw, N, H, W, k, bf, workspace=ws), fl / 1e3, "TFLOP/s")
         del x0, x1, out
 
-if what in ("attn", "all"):
-    for N, S in ((8, 16384), (32, 1024)):
+if what in ("attn", "attn32", "all"):
+    for N, S in (((32, 16384),) if what == "attn32" else ((8, 16384), (32, 1024))):
         C = 128
         qkv = torch.randn(N, S, 3 * C, device=dev).to(bf)
         out = torch.empty(N, S, C, dtype=bf, device=dev)
