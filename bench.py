@@ -222,6 +222,11 @@ def run_ours(args):
         t = sum(a.elapsed_time(b) for a, b, _ in lst)
         fam[name] = {"ms": t, "work": sum(w for _, _, w in lst), "launches": len(lst)}
     peaks = _peaks()
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
     roof, fam_out = None, {}
     tot = sum(f["ms"] for f in fam.values()) or 1.0
     for name, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
@@ -232,7 +237,8 @@ def run_ours(args):
                          "achieved": ach, "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak}
         if roof is None:
             roof = {"kernel": name, "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak, "traffic": None,
+                    "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak,
+                    "traffic": traffic.get(name, {}).get("traffic_bytes"), "traffic_detail": traffic.get(name),
                     "peak_source": peaks["source"] + (" sustained bf16 (kernel timed inside a long step)" if tensor else " copy bandwidth"),
                     "share_of_timed_kernels": f["ms"] / tot}
     # ---- CFG sampling (the second half of BASELINE.json's metric): configs[3] shape, a bounded number of the 1000 steps ----

@@ -326,8 +326,11 @@ extern "C" int hd_gn_bwd_reduce(int dtype, const void* in0, int C0, const void* 
 template <typename T>
 __device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& x, const GnParams& g, const T* dy, const double* gsums, const T* add,
                                                   const T* acc0, const T* acc1, T* dx0, T* dx1, int64_t pix_per_block, int n, int blk,
-                                                  float* s_mean, float* s_rstd, float* s_a, float* s_b) {
+                                                  float* s_mean, float* s_rstd, float* s_a, float* s_b,
+                                                  float* cs_total, float* cs_per_n, int64_t cs_ld, int cs_n, float* s_cs) {
     constexpr int V = Vec<T>::N;
+    const bool want_cs = cs_total || cs_per_n;     // column sums of dx: the bias / embedding-add gradients of the producing conv
+    if (want_cs) for (int i = threadIdx.x; i < g.C; i += blockDim.x) s_cs[i] = 0.f;
     gn_load_stats(g, n, s_mean, s_rstd);
     const double m = (double)(g.C / g.G) * (double)g.HW;
     for (int i = threadIdx.x; i < g.G; i += blockDim.x) {
@@ -358,6 +361,9 @@ __device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& x, const GnPara
     const int64_t p0 = blk * pix_per_block;
     const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
     const bool drop = g.p_drop > 0.f;
+    float cs[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) cs[k] = 0.f;
     constexpr int U = 2;
     for (int64_t pb = p0 + sub; pb < p1; pb += (int64_t)U * ppi) {
       typename Vec<T>::raw xr[U], dr[U], ar[U], cr[U];
@@ -393,16 +399,32 @@ __device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& x, const GnPara
 #pragma unroll
             for (int k = 0; k < V; ++k) r[k] += t[k]; }
         vec_store(dx + o, r);
+#pragma unroll
+        for (int k = 0; k < V; ++k) cs[k] += r[k];
       }
+    }
+    if (want_cs) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) atomicAdd(&s_cs[c0 + k], cs[k]);
     }
     }
     __syncthreads();                              // the shared statistics may be reused by the caller's next work item
+    if (want_cs) {
+        for (int i = threadIdx.x; i < cs_n; i += blockDim.x) {      // only the leading cs_n channels (the first source tensor)
+            if (cs_per_n) atomicAdd(cs_per_n + (int64_t)n * cs_ld + i, s_cs[i]);
+            if (cs_total) atomicAdd(cs_total + i, s_cs[i]);
+        }
+        __syncthreads();
+    }
 }
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> x, GnParams g, const T* dy, const double* gsums, const T* add,
-                                                           const T* acc0, const T* acc1, T* dx0, T* dx1, int64_t pix_per_block) {
+                                                           const T* acc0, const T* acc1, T* dx0, T* dx1, int64_t pix_per_block,
+                                                           float* cs_total, float* cs_per_n, int64_t cs_ld, int cs_n) {
     __shared__ float s_mean[64], s_rstd[64], s_a[64], s_b[64];
-    gn_bwd_apply_body<T>(x, g, dy, gsums, add, acc0, acc1, dx0, dx1, pix_per_block, blockIdx.y, blockIdx.x, s_mean, s_rstd, s_a, s_b);
+    extern __shared__ float s_cs[];               // [C] column sums of dx of this block
+    gn_bwd_apply_body<T>(x, g, dy, gsums, add, acc0, acc1, dx0, dx1, pix_per_block, blockIdx.y, blockIdx.x, s_mean, s_rstd, s_a, s_b,
+                         cs_total, cs_per_n, cs_ld, cs_n, s_cs);
 }
 
 // ------------------------------- backward, both passes in one launch ------------------------
@@ -432,7 +454,8 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(Src2<T> x, GnParams g
             gn_bwd_reduce_body<T>(x, g, dy, pix_per_block, gsums, dgamma, dbeta, n0 + vb / chunks, vb % chunks, s_mean, s_rstd, sg, s_ch);
         hd_grid_barrier(counter, ++round * gridDim.x);
         for (int vb = blockIdx.x; vb < nimg * chunks; vb += gridDim.x)
-            gn_bwd_apply_body<T>(x, g, dy, gsums, add, acc0, acc1, dx0, dx1, pix_per_block, n0 + vb / chunks, vb % chunks, s_mean, s_rstd, s_a, s_b);
+            gn_bwd_apply_body<T>(x, g, dy, gsums, add, acc0, acc1, dx0, dx1, pix_per_block, n0 + vb / chunks, vb % chunks, s_mean, s_rstd, s_a, s_b,
+                                 nullptr, nullptr, 0, 0, s_ch);
     }
 }
 template <typename T>
@@ -477,23 +500,27 @@ extern "C" int hd_gn_bwd_fused(int dtype, const void* in0, int C0, const void* i
 }
 template <typename T>
 static int gn_bwd_apply_t(const void* in0, int C0, const void* in1, int C1, GnParams g, const void* dy, const double* gsums,
-                          const void* add, const void* acc0, const void* acc1, void* dx0, void* dx1, cudaStream_t st) {
+                          const void* add, const void* acc0, const void* acc1, void* dx0, void* dx1, float* cs_total, float* cs_per_n,
+                          int64_t cs_ld, int cs_n, cudaStream_t st) {
     int rc = gn_check<T>(C0, C1, g.G); if (rc) return rc;
     int ppi = 256 / (g.C / Vec<T>::N), chunks;
     int64_t ppb = pick_chunk(g.N, g.HW, ppi, &chunks);
-    gn_bwd_apply_kernel<T><<<dim3((unsigned)chunks, g.N), 256, 0, st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (const T*)dy, gsums,
-                                                                  (const T*)add, (const T*)acc0, (const T*)acc1, (T*)dx0, (T*)dx1, ppb);
+    gn_bwd_apply_kernel<T><<<dim3((unsigned)chunks, g.N), 256, g.C * sizeof(float), st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (const T*)dy, gsums,
+                                                                  (const T*)add, (const T*)acc0, (const T*)acc1, (T*)dx0, (T*)dx1, ppb,
+                                                                  cs_total, cs_per_n, cs_ld, cs_n);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }
 extern "C" int hd_gn_bwd_apply(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G,
                                const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
                                uint64_t seed, const void* dy, const double* gsums, const void* add, const void* acc0,
-                               const void* acc1, void* dx0, void* dx1, cudaStream_t stream) {
+                               const void* acc1, void* dx0, void* dx1, float* cs_total, float* cs_per_n, int64_t cs_ld,
+                               int cs_n, cudaStream_t stream) {
     HD_REQUIRE(in0 && sums && gamma && beta && dy && gsums && dx0 && (C1 == 0 || (in1 && dx1)));
+    HD_REQUIRE(cs_n >= 0 && cs_n <= C0 + C1);
     GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
-    if (dtype == HD_F32) return gn_bwd_apply_t<float>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, stream);
-    if (dtype == HD_BF16) return gn_bwd_apply_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, stream);
+    if (dtype == HD_F32) return gn_bwd_apply_t<float>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, cs_total, cs_per_n, cs_ld, cs_n, stream);
+    if (dtype == HD_BF16) return gn_bwd_apply_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, cs_total, cs_per_n, cs_ld, cs_n, stream);
     return HD_ERR_ARG;
 }
 

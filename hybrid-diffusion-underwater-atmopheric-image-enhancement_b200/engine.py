@@ -440,8 +440,9 @@ class UNetBase(nn.Module):
                  Cout_pad=Cout if out_nchw and Cout != spec.real_cout else None)
         return out
 
-    def _wgrad(self, st, spec, x0, x1, dy, in_nchw=False, dy_nchw=False):
-        """weight gradient into gpk (packed layout) + bias gradient (column sums of dy)."""
+    def _wgrad(self, st, spec, x0, x1, dy, in_nchw=False, dy_nchw=False, bias_done=False):
+        """weight gradient into gpk (packed layout) + bias gradient (column sums of dy; `bias_done`: the producer of dy
+        already accumulated them, see _gn_bwd)."""
         ops = _ops.get()
         if in_nchw:
             N, _, H, W = x0.shape
@@ -450,7 +451,7 @@ class UNetBase(nn.Module):
         dw = st.gpk[spec.w_off // 2: spec.w_off // 2 + spec.n_w]
         ops.wgrad(x0, x1, spec.P_in, dy, spec.P_out, dw, N, H, W, spec.k, self.compute_dtype, in_nchw=in_nchw, dy_nchw=dy_nchw,
                   alg_frac=spec.alg_frac)
-        if spec.has_bias:
+        if spec.has_bias and not bias_done and id(spec) not in st.bias_done:
             C = spec.Cout                       # physical channels of dy (bias is per physical channel)
             db = st.gpk[st.n_dw + spec.b_off: st.n_dw + spec.b_off + C]
             if dy_nchw:
@@ -468,14 +469,18 @@ class UNetBase(nn.Module):
         ops.gn_apply(x0, x1, N, H * W, GN_GROUPS, sums, gn.weight, gn.bias, GN_EPS, act, p_drop, seed, out)
         return out, sums
 
-    def _gn_bwd(self, st, x0, x1, gn, sums, act, p_drop, seed, dy, add=None, acc0=None, acc1=None):
+    def _gn_bwd(self, st, x0, x1, gn, sums, act, p_drop, seed, dy, add=None, acc0=None, acc1=None, cs_total=None, cs_per_n=None,
+                cs_n=None):
+        """cs_total / cs_per_n: accumulate the column sums of the returned gradient (bias and embedding-add gradients of
+        the convolution that produced x) inside the apply pass instead of re-reading the gradient."""
         ops = _ops.get()
         N, H, W = x0.shape[:3]
         gs = torch.empty((N, GN_GROUPS, 2), dtype=torch.float64, device=x0.device)
         dx0 = torch.empty_like(x0)
         dx1 = None if x1 is None else torch.empty_like(x1)
         ops.gn_bwd(x0, x1, N, H * W, GN_GROUPS, sums, gn.weight, gn.bias, GN_EPS, act, p_drop, seed, dy, gs,
-                   st.grad_view(gn.weight), st.grad_view(gn.bias), add, acc0, acc1, dx0, dx1)
+                   st.grad_view(gn.weight), st.grad_view(gn.bias), add, acc0, acc1, dx0, dx1, cs_total=cs_total, cs_per_n=cs_per_n,
+                   cs_n=cs_n)
         return dx0, dx1
 
     def _res_fwd(self, st, rb: ResBlock, idx, x0, x1, emb_all, save, training):
@@ -511,7 +516,18 @@ class UNetBase(nn.Module):
             ctx.update(x0=x0, x1=x1, a1=a1, sums1=sums1, h1=h1, a2=a2, sums2=sums2, h2=h2, p_drop=p_drop, seed=seed, idx=idx)
         return out, ctx
 
-    def _res_bwd(self, st, rb: ResBlock, ctx, d_out, d_emb_all, acc0):
+    def _bias_view(self, st, spec, n):
+        return st.gpk[st.n_dw + spec.b_off: st.n_dw + spec.b_off + n]
+
+    def _claim_bias(self, st, spec):
+        """The caller promises to accumulate the column sums of `spec`'s output gradient itself (inside a GroupNorm
+        backward apply pass); the later _wgrad(spec, ...) then skips its own pass over that gradient."""
+        st.bias_done.add(id(spec))
+        return self._bias_view(st, spec, spec.Cout)
+
+    def _res_bwd(self, st, rb: ResBlock, ctx, d_out, d_emb_all, acc0, prev_spec=None):
+        """prev_spec: the convolution whose output is this block's (first) input; its bias gradient = column sums of the
+        gradient this block returns, accumulated by the final GroupNorm backward."""
         ops = _ops.get()
         sp = st.blocks[id(rb)]
         x0, x1 = ctx["x0"], ctx["x1"]
@@ -524,24 +540,30 @@ class UNetBase(nn.Module):
             ops.attn_bwd(ctx["qkv"], ctx["o"], d_o, ctx["lse"], delta, dqkv, N, H * W, C)
             self._wgrad(st, sp["qkv"], ctx["g"], None, dqkv)
             d_g = self._conv(st, sp["qkv"], dqkv, dgrad=True)
-            d_h2, _ = self._gn_bwd(st, ctx["h2"], None, rb.attn.group_norm, ctx["sums3"], 0, 0.0, 0, d_g, add=d_out)
+            d_h2, _ = self._gn_bwd(st, ctx["h2"], None, rb.attn.group_norm, ctx["sums3"], 0, 0.0, 0, d_g, add=d_out,
+                                   cs_total=self._claim_bias(st, sp["conv2"]))
         else:
             d_h2 = d_out
         self._wgrad(st, sp["conv2"], ctx["a2"], None, d_h2)
         d_a2 = self._conv(st, sp["conv2"], d_h2, dgrad=True)
-        d_h1, _ = self._gn_bwd(st, ctx["h1"], None, rb.block2[0], ctx["sums2"], 1, ctx["p_drop"], ctx["seed"], d_a2)
-        # conv1: weight grad (+ bias via column sums), embedding-add gradient per sample
-        self._wgrad(st, sp["conv1"], ctx["a1"], None, d_h1)
-        N, H, W, C = d_h1.shape
+        # d_h1 = gradient of conv1's output: its column sums are conv1's bias gradient (total) and the gradient of the
+        # per-sample embedding add (per image); both come out of the GroupNorm apply pass
+        c1 = sp["conv1"]
+        C = c1.Cout
         eo = st.emb_offs[ctx["idx"]]
-        ops.colsum(d_h1, N, H * W, C, d_emb_all[:, eo:eo + C], None)
+        db1 = st.gpk[st.n_dw + c1.b_off: st.n_dw + c1.b_off + C]
+        d_h1, _ = self._gn_bwd(st, ctx["h1"], None, rb.block2[0], ctx["sums2"], 1, ctx["p_drop"], ctx["seed"], d_a2,
+                               cs_total=db1, cs_per_n=d_emb_all[:, eo:eo + C])
+        self._wgrad(st, c1, ctx["a1"], None, d_h1, bias_done=True)
         d_a1 = self._conv(st, sp["conv1"], d_h1, dgrad=True)
         if "shortcut" in sp:
             self._wgrad(st, sp["shortcut"], x0, x1, d_h2)
             add = self._conv(st, sp["shortcut"], d_h2, dgrad=True)
         else:
             add = d_h2
-        return self._gn_bwd(st, x0, x1, rb.block1[0], ctx["sums1"], 1, 0.0, 0, d_a1, add=add, acc0=acc0)
+        cs = None if prev_spec is None else self._claim_bias(st, prev_spec)
+        return self._gn_bwd(st, x0, x1, rb.block1[0], ctx["sums1"], 1, 0.0, 0, d_a1, add=add, acc0=acc0, cs_total=cs,
+                            cs_n=x0.shape[-1])
 
     def _run_forward(self, x, t, labels, save):
         ops = _ops.get()
@@ -645,6 +667,7 @@ class UNetBase(nn.Module):
         else:
             st.flat_grad.zero_()
         st.gpk[st.n_dw:].zero_()
+        st.bias_done = set()
         f32 = dict(dtype=torch.float32, device=dev)
         d_emb_all = torch.zeros((N, st.emb_total), **f32)
         reducer = None
@@ -676,7 +699,15 @@ class UNetBase(nn.Module):
                 acc0 = None
                 if not is_up and li <= n_down:
                     acc0 = dskip.pop(li, None)
-                d_h, d_sk = self._res_bwd(st, mod, c, d_h, d_emb_all, acc0)
+                # the convolution that produced this block's first input (the module before it; the head for the first)
+                if li == 0:
+                    prev_spec = st.head
+                else:
+                    pm = mods[li - 1]
+                    psp = st.blocks[id(pm)]
+                    prev_spec = psp["down"] if isinstance(pm, DownSample) else psp["conv"] if isinstance(pm, UpSample) \
+                        else psp["proj"] if "proj" in psp else psp["conv2"]
+                d_h, d_sk = self._res_bwd(st, mod, c, d_h, d_emb_all, acc0, prev_spec=prev_spec)
                 if is_up:
                     dskip[next_skip] = d_sk
                     next_skip += 1

@@ -162,13 +162,14 @@ class CudaOps:
         self._t1(e0, "gn_apply", float(2 * N * HW * (C0 + C1) * x0.element_size()))
 
     def gn_bwd(self, x0, x1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, dy, gsums, dgamma, dbeta,
-               add, acc0, acc1, dx0, dx1):
-        """dgamma/dbeta accumulate; dx0/dx1 are overwritten with dx (+ add + acc0/acc1)."""
+               add, acc0, acc1, dx0, dx1, cs_total=None, cs_per_n=None, cs_n=None):
+        """dgamma/dbeta accumulate; dx0/dx1 are overwritten with dx (+ add + acc0/acc1).  cs_total[c] / cs_per_n[n, c]
+        (optional, accumulate) receive the column sums of dx for the leading cs_n channels (default: all)."""
         C0, C1 = x0.shape[-1], 0 if x1 is None else x1.shape[-1]
         dt = _DT[x0.dtype]
         e0 = self._t0()
         a = (dt, _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _p(gamma), _p(beta), eps, int(act), float(p_drop), int(seed), _p(dy))
-        if self.gn_fused:
+        if self.gn_fused and cs_total is None and cs_per_n is None:
             if self._gn_counter is None or self._gn_counter.device != x0.device:
                 self._gn_counter = torch.zeros(1, dtype=torch.int32, device=x0.device)
             _lib.check(self.lib.hd_gn_bwd_fused(*a, _p(gsums), _p(dgamma), _p(dbeta), _p(add), _p(acc0), _p(acc1), _p(dx0), _p(dx1),
@@ -176,7 +177,9 @@ class CudaOps:
             self.launches += 1
         else:
             _lib.check(self.lib.hd_gn_bwd_reduce(*a, _p(gsums), _p(dgamma), _p(dbeta), _stream()), "hd_gn_bwd_reduce")
-            _lib.check(self.lib.hd_gn_bwd_apply(*a, _p(gsums), _p(add), _p(acc0), _p(acc1), _p(dx0), _p(dx1), _stream()), "hd_gn_bwd_apply")
+            _lib.check(self.lib.hd_gn_bwd_apply(*a, _p(gsums), _p(add), _p(acc0), _p(acc1), _p(dx0), _p(dx1), _p(cs_total), _p(cs_per_n),
+                                                0 if cs_per_n is None else cs_per_n.stride(0),
+                                                (C0 + C1) if cs_n is None else int(cs_n), _stream()), "hd_gn_bwd_apply")
             self.launches += 2
         nt = 5 + (add is not None) + (acc0 is not None)       # x, dy twice; dx once; optional addends
         self._t1(e0, "gn_bwd", float(nt * N * HW * (C0 + C1) * x0.element_size()))

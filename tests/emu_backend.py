@@ -122,7 +122,7 @@ class EmuOps:
         self.launches += 1
 
     def gn_bwd(self, x0, x1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, dy, gsums, dgamma, dbeta,
-               add, acc0, acc1, dx0, dx1):
+               add, acc0, acc1, dx0, dx1, cs_total=None, cs_per_n=None, cs_n=None):
         assert p_drop == 0
         x = self._cat(x0, x1).reshape(N, HW, -1).clone().requires_grad_(True)
         gam = gamma.detach().float().clone().requires_grad_(True)
@@ -150,6 +150,13 @@ class EmuOps:
             if acc1 is not None:
                 d1 = d1 + acc1.float().reshape(N, HW, -1)
             dx1.copy_(d1.reshape(dx1.shape).to(dx1.dtype))
+        if cs_total is not None or cs_per_n is not None:
+            full = d0 if x1 is None else torch.cat([d0, d1], -1)
+            cs = full.reshape(N, HW, C).sum(1)[:, :(C if cs_n is None else cs_n)]
+            if cs_per_n is not None:
+                cs_per_n += cs
+            if cs_total is not None:
+                cs_total += cs.sum(0)
         self.launches += 2
 
     def colsum(self, t, N, HW, C, per_n, total, nchw=False):
