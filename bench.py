@@ -152,6 +152,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/hdiff_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     B, res = args.batch, args.res
     torch.manual_seed(0)                                   # identical replicas
