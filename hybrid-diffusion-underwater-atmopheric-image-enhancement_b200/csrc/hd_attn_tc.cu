@@ -11,6 +11,7 @@
 // S_{j+1} is issued as soon as S_j has been read into registers, so the tensor pipe works under the exponentials.
 // Two CTAs fit one SM (256 TMEM columns and ~99 KB of shared memory each), which overlaps the rest.
 #include "hd_tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -199,6 +200,203 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnFwdPara
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward, second generation (used when S % 256 == 0): one CTA per SM owns TWO 128-row query groups.
+//   * Q lives in TENSOR memory (written once by the softmax threads), so the score MMAs read only the K tile from shared
+//     memory: S = Q K^T with A from TMEM.  P is written in place over the first half of the score columns.
+//   * every K/V tile in shared memory serves both groups: half the TMA traffic per query row.
+//   Shared-memory traffic per (128 queries x 64 keys) drops from 96 KB (first generation, smem-bandwidth bound) to 48 KB.
+//   * the two groups ping-pong: while the softmax warps of one group work, the tensor pipe runs the other group's MMAs.
+// warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: softmax of group 0, warps 6-9: softmax of group 1.
+// TMEM (512 columns): group g at g*256: S/P 64 | Q 64 | O 128.
+// ---------------------------------------------------------------------------------------------
+constexpr int kF2Threads = 64 + 256;
+constexpr int kF2Stages = 6;
+constexpr uint32_t kF2S = 0, kF2Q = 64, kF2O = 128, kF2Group = 256;
+
+__global__ void __launch_bounds__(kF2Threads, 1)
+attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __nv_bfloat16* __restrict__ qkv, const AttnFwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sKV = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kF2Stages * kStageBytes);
+    uint64_t* kv_full = bars;                     // [6]
+    uint64_t* kv_empty = bars + kF2Stages;        // [6]
+    uint64_t* q_ready = bars + 2 * kF2Stages;     // [2]
+    uint64_t* s_full = q_ready + 2;               // [2]
+    uint64_t* p_full = q_ready + 4;               // [2]
+    uint64_t* pv_done = q_ready + 6;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ready + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 2 * BM, n = blockIdx.y;
+    const int T = p.tiles;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapQKV);
+        for (int s = 0; s < kF2Stages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(&q_ready[g], 4); mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4); mbar_init(&pv_done[g], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int j = 0; j < T; ++j) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&kv_full[stage], kStageBytes);
+                uint8_t* st = sKV + stage * kStageBytes;
+                for (int blk = 0; blk < 2; ++blk) tma_load_3d(st + blk * 8192, &mapQKV, &kv_full[stage], D + blk * 64, j * BN, n);
+                for (int blk = 0; blk < 2; ++blk) tma_load_3d(st + kKBytes + blk * 8192, &mapQKV, &kv_full[stage], 2 * D + blk * 64, j * BN, n);
+                if (++stage == kF2Stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);
+            const uint32_t idesc_pv = umma_idesc_bf16(BM, D, 0, 1);
+            // S_g = Q_g K^T: A = Q_g from tensor memory (8 columns per 16 channels), B = K tile (K-major) of `stage`
+            auto issue_s = [&](int g, int stage) {
+                const uint32_t aK = smem_u32(sKV + stage * kStageBytes);
+                const uint32_t tg = tmem_base + g * kF2Group;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int blk = kk >> 2, sub = kk & 3;
+                    umma_bf16_ts(tg + kF2S, tg + kF2Q + kk * 8, umma_smem_desc(aK + blk * 8192 + sub * 32, 16, 1024), idesc_s, kk != 0);
+                }
+                umma_commit(&s_full[g]);
+            };
+            mbar_wait(&q_ready[0], 0);
+            mbar_wait(&q_ready[1], 0);
+            tc_fence_after();
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            int stage = 0, nstage = 1; uint32_t nphase = 0;      // stage of tile j, stage / phase of tile j + 1
+            for (int j = 0; j < T; ++j) {
+                const uint32_t aV = smem_u32(sKV + stage * kStageBytes + kKBytes);
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t tg = tmem_base + g * kF2Group;
+                    mbar_wait(&p_full[g], j & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16_ts(tg + kF2O, tg + kF2S + kk * 8, umma_smem_desc(aV + kk * 2048, 8192, 1024), idesc_pv, (j | kk) != 0);
+                    umma_commit(&pv_done[g]);
+                    if (g == 1) umma_commit(&kv_empty[stage]);   // every MMA that reads tile j has been issued
+                    if (j + 1 < T) {
+                        if (g == 0) { mbar_wait(&kv_full[nstage], nphase); tc_fence_after(); }
+                        issue_s(g, nstage);                      // its P (in place) was consumed by the P V just issued
+                    }
+                }
+                stage = nstage;
+                if (++nstage == kF2Stages) { nstage = 0; nphase ^= 1; }
+            }
+        }
+    } else {
+        const int g = (warp - 2) >> 2;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + g * kF2Group;
+        const long long grow = (long long)n * p.S + q0 + g * BM + row;
+        {   // this thread's query row -> tensor memory (column c = channels 2c, 2c+1)
+            const uint4* src = reinterpret_cast<const uint4*>(qkv + grow * (3 * D));
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                uint32_t q[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 v = __ldg(src + hlf * 8 + i);
+                    q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
+                }
+                tmem_st32(lane_base + kF2Q + hlf * 32, q);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_ready[g]);
+        }
+        const float sl2 = p.scale_log2;
+        float m_ref = 0.f, l = 0.f;
+        for (int j = 0; j < T; ++j) {
+            mbar_wait(&s_full[g], j & 1);
+            tc_fence_after();
+            uint32_t v[64];
+            tmem_ld32(lane_base + kF2S, v);
+            tmem_ld32(lane_base + kF2S + 32, v + 32);
+            tmem_wait_ld();
+            float mx = __uint_as_float(v[0]);
+#pragma unroll
+            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            mx *= sl2;
+            if (j == 0) {
+                m_ref = mx;
+            } else {
+                const bool grow_m = mx > m_ref + kRescaleThreshold;
+                if (__any_sync(0xffffffffu, grow_m)) {
+                    float alpha = 1.f;
+                    if (grow_m) { alpha = fast_exp2(m_ref - mx); m_ref = mx; l *= alpha; }
+                    // O is at rest: S_j completed, and P_{j-1} V was issued before S_j on the in-order tensor pipe
+#pragma unroll 1
+                    for (int c = 0; c < D; c += 32) {
+                        uint32_t o[32];
+                        tmem_ld32(lane_base + kF2O + c, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(lane_base + kF2O + c, o);
+                    }
+                    tmem_wait_st();
+                }
+            }
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float a = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sl2, -m_ref));
+                const float b = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_ref));
+                l += a + b;
+                pk[i] = pack_bf16x2(a, b);
+            }
+            tmem_st32(lane_base + kF2S, pk);          // in place: all 64 score columns of this row are in registers
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[g]);
+        }
+        mbar_wait(&pv_done[g], (T - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.f / l;
+        __nv_bfloat16* orow = p.out + grow * D;
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(lane_base + kF2O + c, o);
+            tmem_wait_ld();
+            uint4* dst = reinterpret_cast<uint4*>(orow + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 w;
+                w.x = pack_bf16x2(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+                w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+                w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+                w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+                dst[i] = w;
+            }
+        }
+        p.lse[grow] = (m_ref + log2f(l)) * 0.6931471805599453f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 int make_qkv_map(CUtensorMap* m, const void* qkv, int N, int S, int C3, int box_rows) {
@@ -470,6 +668,18 @@ extern "C" int hd_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int
     if (!attr_set) {
         if (cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(attn_fwd_tc_kernel)"); return HD_ERR_CUDA; }
         attr_set = true;
+    }
+    static const bool use_v2 = !(getenv("HDIFF_ATTN_FWD_V1"));
+    if (use_v2 && S % (2 * BM) == 0) {
+        const size_t smem2 = kF2Stages * kStageBytes + 1024 + 32 * 8;
+        static bool attr2 = false;
+        if (!attr2) {
+            if (cudaFuncSetAttribute(attn_fwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(attn_fwd2_tc_kernel)"); return HD_ERR_CUDA; }
+            attr2 = true;
+        }
+        attn_fwd2_tc_kernel<<<dim3(S / (2 * BM), N), kF2Threads, smem2, stream>>>(m, (const __nv_bfloat16*)qkv, p);
+        HD_CHECK_LAUNCH();
+        return HD_OK;
     }
     attn_fwd_tc_kernel<<<dim3(S / BM, N), kThreads, smem, stream>>>(m, p);
     HD_CHECK_LAUNCH();
