@@ -434,6 +434,7 @@ struct AttnBwdParams {
     float scale_log2, scale;
     const float2* stats;
     __nv_bfloat16* dqkv;
+    const __nv_bfloat16* qkv; const __nv_bfloat16* dout;
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -448,17 +449,24 @@ constexpr int kBwdThreads = 64 + 256;
 template <bool kDQ>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO, const AttnBwdParams p) {
+    // dQ pass: only 384 TMEM columns are needed for scores + accumulator, so the stationary operands (Q, dO) live in the
+    // remaining 128 columns (written once by the element-wise threads) and the score MMAs read just the K / V tile from
+    // shared memory (A from TMEM): they run at the full N = 64 rate instead of being shared-memory bound, and the 64 KB of
+    // shared memory they occupied become three more ring stages.
+    constexpr bool kXT = kDQ;
+    constexpr int kNS = kXT ? 5 : kBwdStages;
+    constexpr uint32_t kColX0 = 384, kColX1 = 448;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sX0 = smem;
     uint8_t* sX1 = smem + kXBytes;
-    uint8_t* sY = smem + 2 * kXBytes;                        // stages of (Y0 16 KB | Y1 16 KB)
-    uint8_t* sStat = sY + kBwdStages * 2 * kYBytes;          // stages of 512 B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + kBwdStages * kStatBytes);
+    uint8_t* sY = smem + (kXT ? 0 : 2 * kXBytes);            // stages of (Y0 16 KB | Y1 16 KB)
+    uint8_t* sStat = sY + kNS * 2 * kYBytes;                 // stages of 512 B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + kNS * kStatBytes);
     uint64_t* x_full = bars;                       // [1]
     uint64_t* y_full = bars + 1;                   // [3]
-    uint64_t* y_empty = bars + 1 + kBwdStages;     // [3]
-    uint64_t* s_full = bars + 1 + 2 * kBwdStages;  // [2]
+    uint64_t* y_empty = bars + 1 + kNS;     // [3]
+    uint64_t* s_full = bars + 1 + 2 * kNS;  // [2]
     uint64_t* p_full = s_full + 2;                 // [2]
     uint64_t* acc_done = s_full + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
@@ -471,8 +479,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapQKV); tma_prefetch_desc(&mapDO);
-        mbar_init(x_full, 1);
-        for (int s = 0; s < kBwdStages; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
+        mbar_init(x_full, kXT ? 8 : 1);               // kXT: one arrival per element-wise warp (operands stored to TMEM)
+        for (int s = 0; s < kNS; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); }
         mbar_init(acc_done, 1);
         fence_barrier_init();
@@ -487,12 +495,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         if (elect_one()) {
             const CUtensorMap* mX1 = kDQ ? &mapDO : &mapQKV;
             const CUtensorMap* mY1 = kDQ ? &mapQKV : &mapDO;
-            mbar_arrive_expect_tx(x_full, 2 * kXBytes);
-            for (int blk = 0; blk < 2; ++blk)
-                for (int half = 0; half < 2; ++half) {
-                    tma_load_3d(sX0 + blk * (kXBytes / 2) + half * 8192, &mapQKV, x_full, cX0 + blk * 64, r0 + half * 64, n);
-                    tma_load_3d(sX1 + blk * (kXBytes / 2) + half * 8192, mX1, x_full, cX1 + blk * 64, r0 + half * 64, n);
-                }
+            if (!kXT) {
+                mbar_arrive_expect_tx(x_full, 2 * kXBytes);
+                for (int blk = 0; blk < 2; ++blk)
+                    for (int half = 0; half < 2; ++half) {
+                        tma_load_3d(sX0 + blk * (kXBytes / 2) + half * 8192, &mapQKV, x_full, cX0 + blk * 64, r0 + half * 64, n);
+                        tma_load_3d(sX1 + blk * (kXBytes / 2) + half * 8192, mX1, x_full, cX1 + blk * 64, r0 + half * 64, n);
+                    }
+            }
             int stage = 0; uint32_t phase = 0;
             for (int j = 0; j < T; ++j) {
                 mbar_wait(&y_empty[stage], phase ^ 1);
@@ -501,7 +511,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
                 for (int blk = 0; blk < 2; ++blk) tma_load_3d(st + blk * 8192, &mapQKV, &y_full[stage], cY0 + blk * 64, j * BN, n);
                 for (int blk = 0; blk < 2; ++blk) tma_load_3d(st + kYBytes + blk * 8192, mY1, &y_full[stage], cY1 + blk * 64, j * BN, n);
                 if (!kDQ) bulk_load_1d(sStat + stage * kStatBytes, p.stats + (long long)n * p.S + j * BN, kStatBytes, &y_full[stage]);
-                if (++stage == kBwdStages) { stage = 0; phase ^= 1; }
+                if (++stage == kNS) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -518,19 +528,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     const int blk = kk >> 2, sub = kk & 3;
-                    umma_bf16(tmem_base + kColSt + b, umma_smem_desc(aX0 + blk * (kXBytes / 2) + sub * 32, 16, 1024),
-                              umma_smem_desc(aY0 + blk * 8192 + sub * 32, 16, 1024), idesc_s, kk != 0);
+                    const uint64_t bd = umma_smem_desc(aY0 + blk * 8192 + sub * 32, 16, 1024);
+                    if (kXT) umma_bf16_ts(tmem_base + kColSt + b, tmem_base + kColX0 + kk * 8, bd, idesc_s, kk != 0);
+                    else umma_bf16(tmem_base + kColSt + b, umma_smem_desc(aX0 + blk * (kXBytes / 2) + sub * 32, 16, 1024), bd, idesc_s, kk != 0);
                 }
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     const int blk = kk >> 2, sub = kk & 3;
-                    umma_bf16(tmem_base + kColdPt + b, umma_smem_desc(aX1 + blk * (kXBytes / 2) + sub * 32, 16, 1024),
-                              umma_smem_desc(aY1 + blk * 8192 + sub * 32, 16, 1024), idesc_s, kk != 0);
+                    const uint64_t bd = umma_smem_desc(aY1 + blk * 8192 + sub * 32, 16, 1024);
+                    if (kXT) umma_bf16_ts(tmem_base + kColdPt + b, tmem_base + kColX1 + kk * 8, bd, idesc_s, kk != 0);
+                    else umma_bf16(tmem_base + kColdPt + b, umma_smem_desc(aX1 + blk * (kXBytes / 2) + sub * 32, 16, 1024), bd, idesc_s, kk != 0);
                 }
                 umma_commit(&s_full[j & 1]);
-                if (++ld_stage == kBwdStages) { ld_stage = 0; ld_phase ^= 1; }
+                if (++ld_stage == kNS) { ld_stage = 0; ld_phase ^= 1; }
             };
             mbar_wait(x_full, 0);
+            tc_fence_after();
             issue_s(0);
             int stage = 0;
             for (int j = 0; j < T; ++j) {
@@ -554,7 +567,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
                                      umma_smem_desc(aY1 + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0);
                 }
                 umma_commit(&y_empty[stage]);
-                if (++stage == kBwdStages) stage = 0;
+                if (++stage == kNS) stage = 0;
             }
             umma_commit(acc_done);
         }
@@ -566,6 +579,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         const float sl2 = p.scale_log2;
         float2 my = make_float2(0.f, 0.f);
         if (kDQ) my = __ldg(p.stats + (long long)n * p.S + r0 + row);
+        if (kXT) {   // this thread's row of Q (h == 0) or dO (h == 1) -> tensor memory, column c = channels 2c, 2c+1
+            const long long grow = (long long)n * p.S + r0 + row;
+            const uint4* src = h == 0 ? reinterpret_cast<const uint4*>(p.qkv + grow * (3 * D))
+                                      : reinterpret_cast<const uint4*>(p.dout + grow * D);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t q[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 v = __ldg(src + hf * 8 + i);
+                    q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
+                }
+                tmem_st32(lane_base + (h == 0 ? kColX0 : kColX1) + hf * 32, q);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(x_full);
+        }
         int stage = 0; uint32_t y_phase = 0;
         for (int j = 0; j < T; ++j) {
             if (!kDQ) mbar_wait(&y_full[stage], y_phase);    // the tile's (lse, delta) pairs were bulk-copied with it
@@ -599,7 +631,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[j & 1]);
-            if (++stage == kBwdStages) { stage = 0; y_phase ^= 1; }
+            if (++stage == kNS) { stage = 0; y_phase ^= 1; }
         }
         mbar_wait(acc_done, 0);
         tc_fence_after();
@@ -702,7 +734,8 @@ extern "C" int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout
     p.scale = 1.f / sqrtf((float)C);
     p.scale_log2 = 1.4426950408889634f * p.scale;
     p.stats = (const float2*)stats; p.dqkv = (__nv_bfloat16*)dqkv;
-    const size_t smem = 2 * kXBytes + kBwdStages * kBwdStageBytes + 1024 + 20 * 8;
+    p.qkv = (const __nv_bfloat16*)qkv; p.dout = (const __nv_bfloat16*)dout;
+    const size_t smem = 168 * 1024;    // key-row pass: 2 x 32 KB + 3 stages; dQ pass: 5 stages (operands in TMEM); + barriers, alignment
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
