@@ -13,6 +13,7 @@
 // + residual, bf16 store.
 #include "hd_tc_common.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -20,7 +21,12 @@ namespace {
 // K block's two tensor copies in ~600 cycles (measured: the kernel ran at a constant ~640 cycles per K block whatever the
 // MMA width), so the K blocks are dealt round-robin to kProducers issuing threads.
 constexpr int kProducers = 4;
-constexpr int kThreads = 192 + 32 * (kProducers - 1);
+// warps 2-9: epilogue.  Two warps per TMEM lane quarter, each taking every other 16-column chunk of the tile: with one warp
+// per scheduler the epilogue (address arithmetic, TMEM loads, packing, stores) took ~3300 of the ~3600 cycles per tile of a
+// K = 576 convolution (ncu: epilogue warps 93 % busy, main loop idle) and was the bottleneck.
+constexpr int kEpiWarps = 8;
+constexpr int kFirstExtraProducer = 2 + kEpiWarps;
+constexpr int kThreads = 32 * (2 + kEpiWarps + kProducers - 1);
 constexpr int kABytes = 128 * 128;     // 128 pixels x 64 bf16
 constexpr int kMaxStages = 8;
 
@@ -31,6 +37,10 @@ struct ConvTcParams {
     const float* bias; const float* emb; long long emb_stride;
     const __nv_bfloat16* res; __nv_bfloat16* out;
     float* out_nchw; int nchw_c;     // tail: store only the first nchw_c (<= 16) channels, fp32 NCHW
+    int txm;                         // 3x3, TH == 1: one (TW+2)-pixel halo box per (tap row, chunk) serves the 3 tap columns
+    int a_slot, a_tx;                // shared-memory bytes reserved for / transferred into the A part of a stage
+    int nprod;                       // issuing threads in use (<= stages: a producer must never be two ring laps ahead,
+                                     // the parity wait on `empty` cannot tell 0 completed phases from 2)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -39,7 +49,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = p.NT * 128;
-    const int stage_bytes = kABytes + b_bytes;
+    const int stage_bytes = p.a_slot + (p.txm ? 3 : 1) * b_bytes;
+    const int stage_tx = p.a_tx + (p.txm ? 3 : 1) * b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;                       // [stages]
     uint64_t* empty = bars + kMaxStages;         // [stages]
@@ -52,7 +63,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -62,8 +73,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
     const int total_tiles = p.m_tiles * p.n_tiles;
 
-    if (warp == 0 || warp >= 6) {
-        const int prod = warp == 0 ? 0 : warp - 5;       // which share of the K blocks this warp's elected thread issues
+    if (warp == 0 || warp >= kFirstExtraProducer) {
+        const int prod = warp == 0 ? 0 : warp - kFirstExtraProducer + 1;   // which share of the K blocks this warp's elected thread issues
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             int turn = 0;                                // global K-block counter modulo kProducers
@@ -74,6 +85,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
                 // K order = (tap row, tap column, parity row, 64-channel chunk); plain counters, no divisions: this
                 // single thread's loop rate bounds how fast shared memory can be filled
+                if (p.txm) {
+                    // shifted-operand mode: the MMA reads the three tap columns out of ONE halo box at row offsets 0 / 1 / 2
+                    // (a tcgen05 shared-memory operand may start at any 128-byte row of a swizzled box, scripts/probe_shift.py).
+                    // A stage then carries 12 MMAs instead of 4 for 1.7x the bytes: the ring is bounded by shared-memory
+                    // capacity x TMA latency, so this raises the MMA work in flight.
+                    const int tap_stride = p.P_in * p.nchunk_c;          // K blocks between two tap columns
+                    for (int ty = 0; ty < 3; ++ty)
+                        for (int py = 0; py < p.P_in; ++py)
+                            for (int cc = 0; cc < p.nchunk_c; ++cc) {
+                                if (turn == prod) {
+                                    mbar_wait(&empty[stage], phase ^ 1);
+                                    mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_tx);
+                                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                                    if (cc < p.nchunk0) tma_load_5d(sa, &mapA0, &full[stage], cc * 64, x0 - 1, py, y0 + ty - 1, n);
+                                    else tma_load_5d(sa, &mapA1, &full[stage], (cc - p.nchunk0) * 64, x0 - 1, py, y0 + ty - 1, n);
+                                    const int kb0 = (ty * 3 * p.P_in + py) * p.nchunk_c + cc;
+                                    for (int tx = 0; tx < 3; ++tx)
+                                        tma_load_2d(sa + p.a_slot + tx * b_bytes, &mapB, &full[stage], (kb0 + tx * tap_stride) * 64, n_tile * p.NT);
+                                }
+                                if (++turn == p.nprod) turn = 0;
+                                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            }
+                    continue;
+                }
                 int kb = 0;
                 for (int ty = 0; ty < p.k; ++ty)
                     for (int tx = 0; tx < p.k; ++tx)
@@ -81,13 +116,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             for (int cc = 0; cc < p.nchunk_c; ++cc, ++kb) {
                                 if (turn == prod) {
                                     mbar_wait(&empty[stage], phase ^ 1);
-                                    mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                                    mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_tx);
                                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                                     if (cc < p.nchunk0) tma_load_5d(sa, &mapA0, &full[stage], cc * 64, x0 + tx - p.pad, py, y0 + ty - p.pad, n);
                                     else tma_load_5d(sa, &mapA1, &full[stage], (cc - p.nchunk0) * 64, x0 + tx - p.pad, py, y0 + ty - p.pad, n);
-                                    tma_load_2d(sa + kABytes, &mapB, &full[stage], kb * 64, n_tile * p.NT);
+                                    tma_load_2d(sa + p.a_slot, &mapB, &full[stage], kb * 64, n_tile * p.NT);
                                 }
-                                if (++turn == kProducers) turn = 0;
+                                if (++turn == p.nprod) turn = 0;
                                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
                             }
             }
@@ -105,11 +140,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    if (p.txm) {
+#pragma unroll
+                        for (int tx = 0; tx < 3; ++tx) {
+                            const uint64_t adesc = umma_smem_desc(sa + tx * 128, 16, 1024);      // halo box, shifted by tx pixels
+                            const uint64_t bdesc = umma_smem_desc(sa + p.a_slot + tx * b_bytes, 16, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tx | k) != 0);
+                        }
+                    } else {
                     const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
-                    const uint64_t bdesc = umma_smem_desc(sa + kABytes, 16, 1024);
+                    const uint64_t bdesc = umma_smem_desc(sa + p.a_slot, 16, 1024);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // 4 x (K = 16): advance 32 bytes inside the 128-byte swizzle atom
                         umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -118,7 +164,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
     } else {
         const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;            // which of the two interleaved sets of 16-column chunks
         const int row = quarter * 32 + lane;
+        const int etid = (warp - 2) * 32 + lane;     // 0 .. 255 among the epilogue threads
         const int ty = row / p.TW, tx = row % p.TW;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -133,19 +181,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             float* add_t = addend + acc * 256;
             {
                 const float* emb_row = p.emb ? p.emb + (long long)n * p.emb_stride : nullptr;
-                for (int c = row; c < p.NT; c += 128) {
+                for (int c = etid; c < p.NT; c += 32 * kEpiWarps) {
                     const int j = n_tile * p.NT + c;
                     float a = p.bias ? __ldg(p.bias + j) : 0.f;
                     if (emb_row) a += __ldg(emb_row + j);
                     add_t[c] = a;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+                asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps only
             }
+            // element offset of this thread's pixel for output-channel 0 of each parity (P_out == 2 stores the four
+            // parities of the transposed convolution through the 2x2 view); hoisted out of the chunk loop
+            const long long pix1 = (((long long)n * p.H + y) * p.W + x) * p.Cout;
+            const long long pix2 = (((long long)n * (2 * p.H) + 2 * y) * (2 * p.W) + 2 * x) * p.Cout;
+            const long long q_dx = p.Cout, q_dy = 2ll * p.W * p.Cout;
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
             if (p.out_nchw) {
-                if (n_tile == 0) {
+                if (n_tile == 0 && half == 0) {
                     uint32_t v[16];
                     tmem_ld16(taddr, v);
                     tmem_wait_ld();
@@ -159,19 +212,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         }
                     }
                 }
-            } else
-            for (int c = 0; c < p.NT; c += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c, v);
-                tmem_wait_ld();
-                if (valid) {
+            } else {
+                auto emit = [&](const uint32_t* v, int c) {
                     const int j = n_tile * p.NT + c;            // logical output channel of v[0]
                     long long off;
                     if (p.P_out == 1) {
-                        off = (((long long)n * p.H + y) * p.W + x) * p.Cout + j;
+                        off = pix1 + j;
                     } else {
                         const int q = j / p.Cout, cph = j - q * p.Cout;
-                        off = (((long long)n * (2 * p.H) + (2 * y + (q >> 1))) * (2 * p.W) + (2 * x + (q & 1))) * p.Cout + cph;
+                        off = pix2 + (q >> 1) * q_dy + (q & 1) * q_dx + cph;
                     }
                     float f[16];
                     const float4* a4 = reinterpret_cast<const float4*>(add_t + c);
@@ -197,6 +246,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
                     uint4* op = reinterpret_cast<uint4*>(p.out + off);
                     op[0] = o0; op[1] = o1;
+                };
+                // this warp's chunks: half*16, half*16 + 32, ...; two TMEM loads in flight per wait
+                for (int c = half * 16; c < p.NT; c += 64) {
+                    uint32_t va[16], vb[16];
+                    const bool two = c + 32 < p.NT;
+                    tmem_ld16(taddr + c, va);
+                    if (two) tmem_ld16(taddr + c + 32, vb);
+                    tmem_wait_ld();
+                    if (valid) {
+                        emit(va, c);
+                        if (two) emit(vb, c + 32);
+                    }
                 }
             }
             tc_fence_before();
@@ -299,16 +360,28 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     else { p.nchunk0 = 2 * C0 / 64; p.nchunk_c = p.nchunk0; }
     p.kblocks = ksize * ksize * P_in * p.nchunk_c;
     const int CinL = (C0 + C1) * P_in * P_in;
-    const int stage_bytes = kABytes + p.NT * 128;
+    p.txm = 0; p.a_slot = kABytes; p.a_tx = kABytes;
+    int stage_bytes = kABytes + p.NT * 128;
+    {   // shifted-operand mode: 3x3, a tile is one 128-pixel row segment, and at least 3 stages fit
+        static const bool txm_off = getenv("HDIFF_CONV_TXM_OFF") != nullptr;
+        const int a_tx = (p.TW + 2) * 128, a_slot = (a_tx + 1023) / 1024 * 1024;
+        const int sb = a_slot + 3 * p.NT * 128;
+        if (!txm_off && ksize == 3 && p.TH == 1 && p.TW == 128 && (200 * 1024) / sb >= 3) {
+            p.txm = 1; p.a_slot = a_slot; p.a_tx = a_tx; stage_bytes = sb;
+            p.kblocks = 3 * P_in * p.nchunk_c;            // stages per tile: one per (tap row, parity row, chunk)
+        }
+    }
     p.stages = (200 * 1024) / stage_bytes; if (p.stages > kMaxStages) p.stages = kMaxStages;
+    p.nprod = p.stages < kProducers ? p.stages : kProducers;
     p.Cout = Cout; p.P_out = P_out;
     p.bias = bias; p.emb = emb; p.emb_stride = emb_stride;
     p.res = (const __nv_bfloat16*)res; p.out = (__nv_bfloat16*)out;
     p.out_nchw = out_nchw_c ? (float*)out : nullptr; p.nchw_c = out_nchw_c;
 
     CUtensorMap mA0, mA1, mB;
-    int rc = hd_make_act_tmap(&mA0, in0, C0, P_in, N, H, W, 64, p.TW, p.TH); if (rc) return rc;
-    if (C1 > 0) { rc = hd_make_act_tmap(&mA1, in1, C1, 1, N, H, W, 64, p.TW, p.TH); if (rc) return rc; }
+    const int box_w = p.txm ? p.TW + 2 : p.TW;
+    int rc = hd_make_act_tmap(&mA0, in0, C0, P_in, N, H, W, 64, box_w, p.TH); if (rc) return rc;
+    if (C1 > 0) { rc = hd_make_act_tmap(&mA1, in1, C1, 1, N, H, W, 64, box_w, p.TH); if (rc) return rc; }
     else mA1 = mA0;
     {
         uint64_t dims[2] = {(uint64_t)ksize * ksize * CinL, (uint64_t)CoutL};

@@ -40,6 +40,15 @@ CONV_CASES = [
     ("convT_s2d_128", 128, 0, 1, 128, 2, 1, 16, 16, 3, False, False),
     ("3x3_wide_w256", 64, 0, 1, 64, 1, 1, 4, 256, 3, False, False),
     ("3x3_ragged_h", 64, 0, 1, 64, 1, 1, 20, 32, 3, False, True),
+    # W >= 128: one 128-pixel row segment per tile; 3x3 convolutions run in shifted-operand mode (one halo box per tap row)
+    ("3x3_rowseg_64_64", 64, 0, 1, 64, 1, 2, 5, 256, 3, True, True),
+    ("3x3_rowseg_concat", 128, 64, 1, 64, 1, 1, 3, 128, 3, True, True),
+    ("3x3_rowseg_128_128", 128, 0, 1, 128, 1, 2, 5, 128, 3, True, True),
+    ("down_rowseg_s2d", 64, 0, 2, 64, 1, 1, 4, 128, 3, False, False),
+    ("convT_rowseg_s2d", 64, 0, 1, 64, 2, 1, 3, 128, 3, False, False),
+    ("3x3_rowseg_n192", 64, 0, 1, 192, 1, 1, 2, 256, 3, False, False),
+    # several tiles per persistent CTA with a 3-stage ring (fewer stages than TMA-issuing warps)
+    ("3x3_rowseg_128_128_many_tiles", 128, 0, 1, 128, 1, 8, 64, 128, 3, True, True),
 ]
 
 
