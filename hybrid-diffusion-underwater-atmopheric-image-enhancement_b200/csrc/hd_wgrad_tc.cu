@@ -31,16 +31,43 @@ struct WgradTcParams {
     int NT, n_tiles, nb;                      // output-channel tile (<= 256), tiles, nb = NT / 64
     int nch_dy, P_dy;                         // 64-channel chunks per parity row of dY view
     int stages;
+    int halo;                                 // 3x3, one-row pixel tiles: the input blocks of a tap row come out of ONE (TW+2)-pixel
+    int max_units;                            //   halo box at row offsets 0/1/2; max_units = halo boxes per stage (over all groups)
     float* ws;                                // [splits][nblocks_padded * 64][CoutL]
     int rows_padded, CoutL;
 };
+
+constexpr int kHaloBytes = 66 * 128;          // [TW + 2 = 66 pixels][64 channels] bf16
+constexpr int kHaloSlot = 9 * 1024;
+
+// Blocks of a CTA's group -> halo units.  Block b (global index blk) is the input shifted by tap (ty, tx), parity row py,
+// channel chunk cc; all blocks with the same (ty, py, cc) read one halo box at pixel offset tx.
+struct GroupLayout {
+    int nunits;
+    int u_cc[8], u_py[8], u_ty[8];            // per unit
+    int b_unit[8], b_tx[8];                   // per block
+};
+__host__ __device__ inline void decode_group(const WgradTcParams& p, int group, GroupLayout* L) {
+    L->nunits = 0;
+    for (int b = 0; b < 2 * p.G; ++b) {
+        int blk = group * 2 * p.G + b;
+        if (blk >= p.nblocks) blk = p.nblocks - 1;
+        const int cc = blk % p.nchunk_c; const int r2 = blk / p.nchunk_c;
+        const int py = r2 % p.P_in; const int tap = r2 / p.P_in;
+        const int ty = tap / 3, tx = tap % 3;
+        int u = -1;
+        for (int i = 0; i < L->nunits; ++i) if (L->u_cc[i] == cc && L->u_py[i] == py && L->u_ty[i] == ty) u = i;
+        if (u < 0) { u = L->nunits++; L->u_cc[u] = cc; L->u_py[u] = py; L->u_ty[u] = ty; }
+        L->b_unit[b] = u; L->b_tx[b] = tx;
+    }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
                 const __grid_constant__ CUtensorMap mapDY, const WgradTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int a_bytes = p.G * 2 * kBlkBytes, b_bytes = p.nb * kBlkBytes;
+    const int a_bytes = p.halo ? p.max_units * kHaloSlot : p.G * 2 * kBlkBytes, b_bytes = p.nb * kBlkBytes;
     const int stage_bytes = a_bytes + b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;
@@ -89,6 +116,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
             const int dy_c0 = (n_tile * p.nb) % p.nch_dy, dy_py0 = (n_tile * p.nb) / p.nch_dy;
             int tx_i = t_begin % p.tiles_x; int r = t_begin / p.tiles_x;
             int ty_i = r % p.tiles_y; int n = r / p.tiles_y;
+            if (p.halo) {
+                GroupLayout L;
+                decode_group(p, group, &L);
+                // copies of a stage: the halo units, then the dY blocks; dealt round-robin to the producers
+                uint32_t my_bytes = 0;
+                for (int i = prod; i < L.nunits + p.nb; i += kProducers) my_bytes += i < L.nunits ? kHaloBytes : kBlkBytes;
+                for (int t = t_begin; t < t_end; ++t) {
+                    const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], my_bytes);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (u < L.nunits && (u % kProducers) == prod) {
+                            if (L.u_cc[u] < p.nchunk0) tma_load_5d(sa + u * kHaloSlot, &mapX0, &full[stage], L.u_cc[u] * 64, x0 - 1, L.u_py[u], y0 + L.u_ty[u] - 1, n);
+                            else tma_load_5d(sa + u * kHaloSlot, &mapX1, &full[stage], (L.u_cc[u] - p.nchunk0) * 64, x0 - 1, L.u_py[u], y0 + L.u_ty[u] - 1, n);
+                        }
+                    }
+                    int cc = dy_c0, py = dy_py0;
+                    for (int b = 0; b < p.nb; ++b) {
+                        if (((L.nunits + b) % kProducers) == prod)
+                            tma_load_5d(sa + a_bytes + b * kBlkBytes, &mapDY, &full[stage], cc * 64, x0, py, y0, n);
+                        if (++cc == p.nch_dy) { cc = 0; ++py; }
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    if (++tx_i == p.tiles_x) { tx_i = 0; if (++ty_i == p.tiles_y) { ty_i = 0; ++n; } }
+                }
+            } else
             for (int t = t_begin; t < t_end; ++t) {
                 const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
                 mbar_wait(&empty[stage], phase ^ 1);
@@ -115,15 +170,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, p.NT, 1, 1);
             int stage = 0; uint32_t phase = 0;
+            // offset of the first block of each 128-row pair inside the A part of a stage, and the distance to its second block
+            uint32_t a_off[4], a_lbo[4];
+            if (p.halo) {
+                GroupLayout L;
+                decode_group(p, group, &L);
+                for (int g = 0; g < 4; ++g) {
+                    if (g < p.G) {
+                        const uint32_t o0 = L.b_unit[2 * g] * kHaloSlot + L.b_tx[2 * g] * 128;
+                        const uint32_t o1 = L.b_unit[2 * g + 1] * kHaloSlot + L.b_tx[2 * g + 1] * 128;
+                        a_off[g] = o0; a_lbo[g] = o1 - o0;            // host guarantees o1 >= o0
+                    } else { a_off[g] = 0; a_lbo[g] = 0; }
+                }
+            } else {
+                for (int g = 0; g < 4; ++g) { a_off[g] = g * 2 * kBlkBytes; a_lbo[g] = kBlkBytes; }
+            }
             for (int s = 0; s < nsteps; ++s) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t sb = sa + a_bytes;
-                for (int g = 0; g < p.G; ++g) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g >= p.G) break;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {    // K = 16 pixels = 2 groups of 8 rows = 2048 bytes
-                        const uint64_t adesc = umma_smem_desc(sa + g * 2 * kBlkBytes + k * 2048, kBlkBytes, 1024);
+                        const uint64_t adesc = umma_smem_desc(sa + a_off[g] + k * 2048, a_lbo[g], 1024);
                         const uint64_t bdesc = umma_smem_desc(sb + k * 2048, kBlkBytes, 1024);
                         umma_bf16(tmem_base + g * p.NT, adesc, bdesc, idesc, (s | k) != 0);
                     }
@@ -219,7 +291,32 @@ bool make_plan(int C0, int C1, int P_in, int Cdy, int P_dy, int N, int H, int W,
     p.G = G;
     p.ngroups = (npairs + G - 1) / G;
     p.rows_padded = p.ngroups * G * 128;
-    const int stage_bytes = (G * 2 + p.nb) * kBlkBytes;
+    int stage_bytes = (G * 2 + p.nb) * kBlkBytes;
+    p.halo = 0; p.max_units = 0;
+    static const bool halo_off = getenv("HDIFF_WGRAD_HALO_OFF") != nullptr;
+    if (!halo_off && k == 3 && p.TH == 1 && p.TW == 64) {
+        // halo mode: the stage shrinks (one box per tap row instead of one per tap), so take the largest G (fewest groups)
+        WgradTcParams q = p;
+        int Gh = 512 / p.NT; if (Gh > 4) Gh = 4; if (Gh > npairs) Gh = npairs;
+        while (Gh > 1 && (npairs + Gh - 2) / (Gh - 1) == (npairs + Gh - 1) / Gh) --Gh;
+        q.G = Gh; q.ngroups = (npairs + Gh - 1) / Gh;
+        bool ok = true; int max_units = 0;
+        for (int g = 0; g < q.ngroups && ok; ++g) {
+            GroupLayout L;
+            decode_group(q, g, &L);
+            if (L.nunits > 8) ok = false;
+            if (L.nunits > max_units) max_units = L.nunits;
+            for (int i = 0; i < Gh && ok; ++i) {           // the second block of a 128-row pair must not lie below the first
+                const int o0 = L.b_unit[2 * i] * kHaloSlot + L.b_tx[2 * i] * 128, o1 = L.b_unit[2 * i + 1] * kHaloSlot + L.b_tx[2 * i + 1] * 128;
+                if (o1 < o0) ok = false;
+            }
+        }
+        const int sb = max_units * kHaloSlot + p.nb * kBlkBytes;
+        if (ok && (200 * 1024) / sb >= 3 && sb < stage_bytes) {
+            p.G = Gh; p.ngroups = q.ngroups; p.rows_padded = p.ngroups * Gh * 128;
+            p.halo = 1; p.max_units = max_units; stage_bytes = sb;
+        }
+    }
     p.stages = (200 * 1024) / stage_bytes; if (p.stages > kMaxStages) p.stages = kMaxStages;
     if (p.stages < 2) return false;
     // split-K over pixel tiles: fill the machine about twice
@@ -254,11 +351,12 @@ extern "C" int hd_wgrad_tc(const void* in0, int C0, const void* in1, int C1, int
     HD_REQUIRE(workspace_bytes >= (long long)p.splits * p.rows_padded * p.CoutL * 4);
     p.ws = (float*)workspace;
     CUtensorMap mX0, mX1, mDY;
-    int rc = hd_make_act_tmap(&mX0, in0, C0, P_in, N, H, W, 64, p.TW, p.TH); if (rc) return rc;
-    if (C1 > 0) { rc = hd_make_act_tmap(&mX1, in1, C1, 1, N, H, W, 64, p.TW, p.TH); if (rc) return rc; }
+    const int box_w = p.halo ? p.TW + 2 : p.TW;
+    int rc = hd_make_act_tmap(&mX0, in0, C0, P_in, N, H, W, 64, box_w, p.TH); if (rc) return rc;
+    if (C1 > 0) { rc = hd_make_act_tmap(&mX1, in1, C1, 1, N, H, W, 64, box_w, p.TH); if (rc) return rc; }
     else mX1 = mX0;
     rc = hd_make_act_tmap(&mDY, dy, Cdy, P_dy, N, H, W, 64, p.TW, p.TH); if (rc) return rc;
-    const int stage_bytes = (p.G * 2 + p.nb) * kBlkBytes;
+    const int stage_bytes = (p.halo ? p.max_units * kHaloSlot : p.G * 2 * kBlkBytes) + p.nb * kBlkBytes;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * kMaxStages + 2) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
