@@ -151,9 +151,11 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # keep stdout to the one JSON line: anything libraries print meanwhile (NCCL's version banner, warnings) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/hdiff_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     B, res = args.batch, args.res
     torch.manual_seed(0)                                   # identical replicas
@@ -284,6 +286,9 @@ def run_ours(args):
                     "nan_flag": int(nan_flag.item())}
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
