@@ -36,7 +36,8 @@ PROTOTYPES = {
     "hd_add_int": [P, I, P],
     "hd_sqnorm": [P, L, P, P],
     "hd_adamw_flat": [P, P, P, P, L, P, F, F, F, F, F, F, I, P],
-    "hd_conv_tc": [P, I, P, I, I, P, P, P, L, P, P, I, I, I, I, I, I, I, P],
+    "hd_conv_tc": [P, I, P, I, I, P, P, P, L, P, P, I, I, I, I, I, I, I, P, P],
+    "hd_gn_group_sums": [P, I, P, I, I, I, P, P],
     "hd_pad_nchw": [P, I, P, I, L, P],
     "hd_probe_shift": [P, P, P, I, I, P],
     "hd_conv_tc_supported": [I, I, I, I, I, I, I, I],

@@ -39,10 +39,14 @@ struct ConvTcParams {
     float* out_nchw; int nchw_c;     // tail: store only the first nchw_c (<= 16) channels, fp32 NCHW
     int txm;                         // 3x3, TH == 1: one (TW+2)-pixel halo box per (tap row, chunk) serves the 3 tap columns
     int a_slot, a_tx;                // shared-memory bytes reserved for / transferred into the A part of a stage
+    double* chan_sums;               // optional [N][Cout][2]: per-image, per-channel sum / sum of squares of the STORED output
+                                     // (the GroupNorm statistics of the next layer, without another pass over the tensor)
     int nprod;                       // issuing threads in use (<= stages: a producer must never be two ring laps ahead,
                                      // the parity wait on `empty` cannot tell 0 completed phases from 2)
 };
 
+template <bool kStats>     // kStats: the epilogue also accumulates p.chan_sums (separate instantiation: the extra registers and
+                           // shuffles must not slow the plain epilogue down)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const ConvTcParams p) {
@@ -58,6 +62,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint64_t* tempty = bars + 2 * kMaxStages + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
     float* addend = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);     // [2][256]: bias + embedding row of a tile
+    float* stat_s = addend + 2 * 256;                                        // [2][256][2]: per-tile channel sums (p.chan_sums)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -187,6 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     if (emb_row) a += __ldg(emb_row + j);
                     add_t[c] = a;
                 }
+                if (kStats) for (int c = etid; c < 2 * p.NT; c += 32 * kEpiWarps) stat_s[acc * 512 + c] = 0.f;
                 asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps only
             }
             // element offset of this thread's pixel for output-channel 0 of each parity (P_out == 2 stores the four
@@ -213,7 +219,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 }
             } else {
-                auto emit = [&](const uint32_t* v, int c) {
+                auto emit = [&](const uint32_t* v, int c, float* f) {
                     const int j = n_tile * p.NT + c;            // logical output channel of v[0]
                     long long off;
                     if (p.P_out == 1) {
@@ -222,7 +228,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const int q = j / p.Cout, cph = j - q * p.Cout;
                         off = pix2 + (q >> 1) * q_dy + (q & 1) * q_dx + cph;
                     }
-                    float f[16];
                     const float4* a4 = reinterpret_cast<const float4*>(add_t + c);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -246,6 +251,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
                     uint4* op = reinterpret_cast<uint4*>(p.out + off);
                     op[0] = o0; op[1] = o1;
+                    // the values as stored (bf16), for the statistics
+                    if (kStats) {
+                        const uint32_t pk[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { f[2 * i] = __uint_as_float(pk[i] << 16); f[2 * i + 1] = __uint_as_float(pk[i] & 0xFFFF0000u); }
+                    }
+                };
+                // column sums over the 32 pixels of this warp by a transposing butterfly: 32 quantities per lane in, the total
+                // of quantity l on lane l out, 31 shuffles (a plain butterfly would take 160)
+                auto stats = [&](const float* f, bool on, int c) {
+                    float r[32];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { r[i] = on ? f[i] : 0.f; r[16 + i] = on ? f[i] * f[i] : 0.f; }
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const bool upper = (lane & step) != 0;
+#pragma unroll
+                        for (int i = 0; i < step; ++i) {
+                            const float send = upper ? r[i] : r[i + step];
+                            const float keep = upper ? r[i + step] : r[i];
+                            r[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+                        }
+                    }
+                    atomicAdd(&stat_s[acc * 512 + (c + (lane & 15)) * 2 + (lane >> 4)], r[0]);
                 };
                 // this warp's chunks: half*16, half*16 + 32, ...; two TMEM loads in flight per wait
                 for (int c = half * 16; c < p.NT; c += 64) {
@@ -254,15 +283,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     tmem_ld16(taddr + c, va);
                     if (two) tmem_ld16(taddr + c + 32, vb);
                     tmem_wait_ld();
+                    float fa[16], fb[16];
                     if (valid) {
-                        emit(va, c);
-                        if (two) emit(vb, c + 32);
+                        emit(va, c, fa);
+                        if (two) emit(vb, c + 32, fb);
+                    }
+                    if (kStats) {
+                        stats(fa, valid, c);
+                        if (two) stats(fb, valid, c + 32);
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (kStats) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");          // every warp's contribution to this tile is in shared memory
+                for (int c = etid; c < 2 * p.NT; c += 32 * kEpiWarps)
+                    atomicAdd(p.chan_sums + ((long long)n * p.Cout + n_tile * p.NT) * 2 + c, (double)stat_s[acc * 512 + c]);
+            }
         }
     }
     tc_fence_before();
@@ -343,7 +382,7 @@ extern "C" int hd_conv_tc_supported(int C0, int C1, int P_in, int Cout, int P_ou
 
 extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int P_in, const void* w, const float* bias,
                           const float* emb, int64_t emb_stride, const void* res, void* out, int Cout, int P_out,
-                          int N, int H, int W, int ksize, int out_nchw_c, cudaStream_t stream) {
+                          int N, int H, int W, int ksize, int out_nchw_c, double* chan_sums, cudaStream_t stream) {
     HD_REQUIRE(in0 && w && out && N > 0);
     HD_REQUIRE(out_nchw_c >= 0 && out_nchw_c <= 16 && (out_nchw_c == 0 || (P_out == 1 && !emb && !res)));
     if (!hd_conv_tc_supported(C0, C1, P_in, Cout, P_out, H, W, ksize)) { hd_set_error("hd_conv_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
@@ -377,6 +416,8 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     p.bias = bias; p.emb = emb; p.emb_stride = emb_stride;
     p.res = (const __nv_bfloat16*)res; p.out = (__nv_bfloat16*)out;
     p.out_nchw = out_nchw_c ? (float*)out : nullptr; p.nchw_c = out_nchw_c;
+    HD_REQUIRE(!chan_sums || (P_out == 1 && out_nchw_c == 0));
+    p.chan_sums = chan_sums;
 
     CUtensorMap mA0, mA1, mB;
     const int box_w = p.txm ? p.TW + 2 : p.TW;
@@ -389,14 +430,18 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
         uint32_t box[2] = {64, (uint32_t)p.NT};
         rc = hd_make_tmap_bf16(&mB, w, 2, dims, str, box); if (rc) return rc;
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 2 * 256 * 4;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 2 * 256 * 4 + 2 * 512 * 4;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(conv_tc_kernel)"); return HD_ERR_CUDA; }
+        if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            hd_set_error("cudaFuncSetAttribute(conv_tc_kernel)"); return HD_ERR_CUDA;
+        }
         attr_set = true;
     }
     int grid = p.m_tiles * p.n_tiles; const int sms = hd_num_sms(); if (grid > sms) grid = sms;
-    conv_tc_kernel<<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
+    if (chan_sums) conv_tc_kernel<true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
+    else conv_tc_kernel<false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }

@@ -150,6 +150,26 @@ extern "C" int hd_gn_stats(int dtype, const void* in0, int C0, const void* in1, 
     return HD_ERR_ARG;
 }
 
+// GroupNorm statistics from per-channel sums that the producing convolutions left behind (hd_conv_tc `chan_sums`):
+// sums[n][g] = sum over the channels of group g of cs[n][c]; the (possibly two-source) channel axis is C0 | C1.
+__global__ void gn_group_sums_kernel(const double* cs0, int C0, const double* cs1, int C1, int N, int G, double* sums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * G) return;
+    const int n = i / G, g = i - n * G, cpg = (C0 + C1) / G;
+    double s = 0.0, ss = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        const double* p = c < C0 ? cs0 + ((long long)n * C0 + c) * 2 : cs1 + ((long long)n * C1 + (c - C0)) * 2;
+        s += p[0]; ss += p[1];
+    }
+    sums[(long long)i * 2] = s; sums[(long long)i * 2 + 1] = ss;
+}
+extern "C" int hd_gn_group_sums(const double* cs0, int C0, const double* cs1, int C1, int N, int G, double* sums, cudaStream_t stream) {
+    HD_REQUIRE(cs0 && sums && N > 0 && G > 0 && C0 > 0 && (C1 == 0 || cs1) && (C0 + C1) % G == 0);
+    gn_group_sums_kernel<<<(N * G + 127) / 128, 128, 0, stream>>>(cs0, C0, cs1, C1, N, G, sums);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+
 // ------------------------------- apply (forward) --------------------------------------------
 // out[n][pix][c] = drop( act( (x - mean) * rstd * gamma + beta ) ); grid (chunks, N).
 // thread <-> fixed channel vector (scale / shift hoisted out of the pixel loop: one FMA per element before the activation)

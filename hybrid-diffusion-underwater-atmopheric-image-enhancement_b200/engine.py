@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 from typing import List, Optional
 
 import torch
@@ -24,6 +25,7 @@ from . import ops as _ops
 
 GN_GROUPS = 32
 GN_EPS = 1e-5
+CONV_EPILOGUE_STATS = os.environ.get("HDIFF_CONV_STATS", "0") == "1"
 
 
 # =============================================================================================
@@ -380,6 +382,8 @@ class UNetBase(nn.Module):
         st.gpk = torch.zeros(st.n_dw + st.n_bpack, dtype=torch.float32, device=dev)
         st.packed_version = None
         st.wgrad_ws = None
+        st.chan, st.chan_pool, st.chan_off = {}, None, 0
+        st.sum_cout = sum(sp.Cout for sp in specs)
         self._state = st
         return st
 
@@ -423,7 +427,19 @@ class UNetBase(nn.Module):
     def _bv(self, st, spec):
         return st.bpack[spec.b_off:spec.b_off + spec.CoutL] if spec.has_bias else None
 
-    def _conv(self, st, spec, x0, x1=None, emb=None, res=None, dgrad=False, in_nchw=False, out_nchw=False):
+    def _chan_alloc(self, st, N, C):
+        """[N][C][2] fp64 zeros out of the per-forward pool (one memset per forward instead of one per convolution)."""
+        n = N * C * 2
+        if st.chan_pool is None or st.chan_off + n > st.chan_pool.numel():
+            st.chan_pool = torch.zeros(max(n, N * 2 * st.sum_cout), dtype=torch.float64, device=st.device)
+            st.chan_off = 0
+        v = st.chan_pool[st.chan_off: st.chan_off + n].view(N, C, 2)
+        st.chan_off += n
+        return v
+
+    def _conv(self, st, spec, x0, x1=None, emb=None, res=None, dgrad=False, in_nchw=False, out_nchw=False, want_stats=False):
+        """want_stats: let the kernel's epilogue leave per-image per-channel (sum, sum of squares) of the output for the
+        GroupNorm that reads it next (tcgen05 path only; otherwise _gn_fwd falls back to the statistics kernel)."""
         ops = _ops.get()
         P_in, P_out = (spec.P_out, spec.P_in) if dgrad else (spec.P_in, spec.P_out)
         Cout = spec.Cin if dgrad else spec.Cout
@@ -435,9 +451,17 @@ class UNetBase(nn.Module):
             out = torch.empty((N, spec.real_cout, H, W), dtype=torch.float32, device=x0.device)
         else:
             out = torch.empty((N, H * P_out, W * P_out, Cout), dtype=self.compute_dtype, device=x0.device)
-        ops.conv(x0, x1, P_in, self._wv(st, spec, dgrad), None if dgrad else self._bv(st, spec), emb, res, out, P_out,
-                 N, H, W, spec.k, in_nchw=in_nchw, out_nchw=out_nchw, alg_frac=spec.alg_frac,
-                 Cout_pad=Cout if out_nchw and Cout != spec.real_cout else None)
+        cs = None
+        # Off by default: measured on B200 the statistics epilogue costs more than the pass it saves (conv 64->64 at 256x256:
+        # 0.216 -> 0.356 ms against 0.08 ms for hd_gn_stats; 128->128 at 128x128: +0.045 ms against 0.046 ms).
+        if (want_stats and CONV_EPILOGUE_STATS and not dgrad and not out_nchw and P_out == 1
+                and self.compute_dtype == torch.bfloat16):
+            cs = self._chan_alloc(st, N, Cout)
+        got = ops.conv(x0, x1, P_in, self._wv(st, spec, dgrad), None if dgrad else self._bv(st, spec), emb, res, out, P_out,
+                       N, H, W, spec.k, in_nchw=in_nchw, out_nchw=out_nchw, alg_frac=spec.alg_frac,
+                       Cout_pad=Cout if out_nchw and Cout != spec.real_cout else None, chan_sums=cs)
+        if cs is not None and got:
+            st.chan[id(out)] = (weakref.ref(out), cs)     # keyed by the tensor OBJECT: an address can be reused after a free
         return out
 
     def _wgrad(self, st, spec, x0, x1, dy, in_nchw=False, dy_nchw=False, bias_done=False):
@@ -464,7 +488,16 @@ class UNetBase(nn.Module):
         N, H, W = x0.shape[:3]
         C = x0.shape[3] + (0 if x1 is None else x1.shape[3])
         sums = torch.empty((N, GN_GROUPS, 2), dtype=torch.float64, device=x0.device)
-        ops.gn_stats(x0, x1, N, H * W, GN_GROUPS, sums)
+        st = self._state
+        def left_behind(t):
+            e = st.chan.get(id(t))
+            return e[1] if e is not None and e[0]() is t else None
+        cs0 = left_behind(x0)
+        cs1 = None if x1 is None else left_behind(x1)
+        if cs0 is not None and (x1 is None or cs1 is not None):
+            ops.gn_group_sums(cs0, cs1, N, GN_GROUPS, sums)          # statistics left behind by the producing convolutions
+        else:
+            ops.gn_stats(x0, x1, N, H * W, GN_GROUPS, sums)
         out = torch.empty((N, H, W, C), dtype=self.compute_dtype, device=x0.device)
         ops.gn_apply(x0, x1, N, H * W, GN_GROUPS, sums, gn.weight, gn.bias, GN_EPS, act, p_drop, seed, out)
         return out, sums
@@ -488,7 +521,7 @@ class UNetBase(nn.Module):
         ctx = {}
         a1, sums1 = self._gn_fwd(x0, x1, rb.block1[0], act=1)
         eo = st.emb_offs[idx]
-        h1 = self._conv(st, sp["conv1"], a1, emb=emb_all[:, eo:eo + rb.out_ch])
+        h1 = self._conv(st, sp["conv1"], a1, emb=emb_all[:, eo:eo + rb.out_ch], want_stats=True)
         p_drop = rb.p_drop if training else 0.0
         seed = 0
         if p_drop > 0:       # host-side counter stream: no device sync, reproducible under torch.manual_seed
@@ -499,7 +532,7 @@ class UNetBase(nn.Module):
             s = self._conv(st, sp["shortcut"], x0, x1)
         else:
             s = x0
-        h2 = self._conv(st, sp["conv2"], a2, res=s)
+        h2 = self._conv(st, sp["conv2"], a2, res=s, want_stats=True)
         out = h2
         if "qkv" in sp:
             ops = _ops.get()
@@ -509,7 +542,7 @@ class UNetBase(nn.Module):
             o = torch.empty_like(h2)
             lse = torch.empty((N, H * W), dtype=torch.float32, device=h2.device)
             ops.attn_fwd(qkv, o, lse, N, H * W, C)
-            out = self._conv(st, sp["proj"], o, res=h2)
+            out = self._conv(st, sp["proj"], o, res=h2, want_stats=True)
             if save:
                 ctx.update(g=g, sums3=sums3, qkv=qkv, o=o, lse=lse)
         if save:
@@ -572,6 +605,7 @@ class UNetBase(nn.Module):
             self.repack()
         training = self.training
         dev = x.device
+        st.chan, st.chan_pool, st.chan_off = {}, None, 0
         assert x.dim() == 4 and x.shape[1] == 3 and x.dtype == torch.float32
         x = x.contiguous()
         N = x.shape[0]
@@ -610,7 +644,7 @@ class UNetBase(nn.Module):
         if st.pad_io:
             xp = torch.empty((N, x.shape[2], x.shape[3], 64), dtype=self.compute_dtype, device=dev)
             ops.pad_nchw(x, xp)
-            h = self._conv(st, st.head, xp)
+            h = self._conv(st, st.head, xp, want_stats=True)
             ctx["x"] = xp
         else:
             h = self._conv(st, st.head, x, in_nchw=True)
@@ -625,7 +659,7 @@ class UNetBase(nn.Module):
             else:
                 sp = st.blocks[id(mod)]["down"]
                 xin = h
-                h = self._conv(st, sp, xin)
+                h = self._conv(st, sp, xin, want_stats=True)
                 c = {"x": xin} if save else None
             bctx.append(c)
             hs.append(h)
@@ -641,7 +675,7 @@ class UNetBase(nn.Module):
                 sp = st.blocks[id(mod)]
                 xin = h
                 u = self._conv(st, sp["convT"], xin)
-                h = self._conv(st, sp["conv"], u)
+                h = self._conv(st, sp["conv"], u, want_stats=True)
                 c = {"x": xin, "u": u} if save else None
             bctx.append(c)
         assert len(hs) == 0 and ri == nrb

@@ -56,7 +56,7 @@ class CudaOps:
 
     # ---- convolution family -------------------------------------------------------------
     def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0,
-             Cout_pad=None):
+             Cout_pad=None, chan_sums=None):
         """out = conv_k(view(x0|x1, P_in)) + bias + emb[:, :, None, None] + res, logical stride 1, 'same' padding.
         w: packed [CoutL][k*k][CinL] in the compute dtype.  H, W are the LOGICAL spatial dims.
         `alg_frac`: share of the packed taps that are real reference taps (space-to-depth views carry zeros);
@@ -75,12 +75,12 @@ class CudaOps:
                 and lib.hd_conv_tc_supported(C0, C1, P_in, Cout, P_out, H, W, k)):
             rc = lib.hd_conv_tc(_p(x0), C0, _p(x1), C1, P_in, _p(w), _p(bias), _p(emb),
                                 0 if emb is None else emb.stride(0), _p(res), _p(out), Cout, P_out,
-                                N, H, W, k, nchw_c, _stream())
+                                N, H, W, k, nchw_c, _p(chan_sums), _stream())
             _lib.check(rc, "hd_conv_tc")
             self.launches += 1
             self.tc_launches += 1
             self._t1(e0, "conv_tc", flops)
-            return
+            return True if chan_sums is not None else None      # True: the per-channel statistics were produced
         rc = lib.hd_conv_simt(dt, _p(x0), C0, _p(x1), C1, P_in, int(in_nchw), _p(w), _p(bias), _p(emb),
                               0 if emb is None else emb.stride(0), _p(res), _p(out), Cout, P_out, nchw_c,
                               N, H, W, k, _stream())
@@ -152,6 +152,12 @@ class CudaOps:
         _lib.check(self.lib.hd_gn_stats(_DT[x0.dtype], _p(x0), C0, _p(x1), C1, N, HW, G, _p(sums), _stream()), "hd_gn_stats")
         self.launches += 1
         self._t1(e0, "gn_stats", float(N * HW * (C0 + C1) * x0.element_size()))
+
+    def gn_group_sums(self, cs0, cs1, N, G, sums):
+        """sums[N][G][2] from per-channel sums cs0 [N][C0][2] (| cs1 [N][C1][2]) left by the producing convolutions."""
+        _lib.check(self.lib.hd_gn_group_sums(_p(cs0), cs0.shape[1], _p(cs1), 0 if cs1 is None else cs1.shape[1], N, G, _p(sums),
+                                             _stream()), "hd_gn_group_sums")
+        self.launches += 1
 
     def gn_apply(self, x0, x1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, out):
         e0 = self._t0()

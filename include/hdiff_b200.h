@@ -45,7 +45,9 @@ int hd_wgrad_simt(int dtype, const void* in0, int C0, const void* in1, int C1, i
 int hd_conv_tc_supported(int C0, int C1, int P_in, int Cout, int P_out, int H, int W, int ksize);
 int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int P_in, const void* w, const float* bias,
                const float* emb, int64_t emb_stride, const void* res, void* out, int Cout, int P_out,
-               int N, int H, int W, int ksize, int out_nchw_c, hd_stream_t stream);
+               int N, int H, int W, int ksize, int out_nchw_c, double* chan_sums, hd_stream_t stream);
+/* chan_sums (optional, accumulates, caller zeroes): [N][Cout][2] fp64 per-image per-channel (sum, sum of squares) of the
+ * stored output — the next GroupNorm's statistics without another pass over the tensor (P_out == 1 only). */
 /* out_nchw_c > 0: `out` is fp32 NCHW [N][out_nchw_c][H][W] and only the first out_nchw_c output channels are stored
  * (the 3-channel tail, ModelCondition.py:251, run as a 64-channel GEMM with zero-padded weights). */
 /* NCHW fp32 [N][Cin<=8][HW] -> NHWC bf16 [N][HW][64], channels >= Cin zero (head input / tail output gradient) */
@@ -73,6 +75,8 @@ int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const flo
  *      (C0 | C1 channels) fuses torch.cat :271 into the normalisation.  sums/gsums = [N][G][2] fp64. ---- */
 int hd_gn_stats(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, double* sums,
                 hd_stream_t stream);
+/* group statistics [N][G][2] from the per-channel sums of one or two source tensors (see hd_conv_tc chan_sums) */
+int hd_gn_group_sums(const double* cs0, int C0, const double* cs1, int C1, int N, int G, double* sums, hd_stream_t stream);
 int hd_gn_apply(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, const double* sums,
                 const float* gamma, const float* beta, float eps, int act, float p_drop, uint64_t seed, void* out,
                 hd_stream_t stream);

@@ -46,7 +46,7 @@ class EmuOps:
         x = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
         return to_logical(x, P_in).permute(0, 3, 1, 2).float()
 
-    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0, Cout_pad=None):
+    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0, Cout_pad=None, chan_sums=None):
         xin = self._logical_in(x0, x1, P_in, in_nchw)
         CinL = xin.shape[1]
         CoutL = w.numel() // (k * k * CinL)
@@ -62,6 +62,12 @@ class EmuOps:
                 y = y + res.float()
             out.copy_(y.to(out.dtype))
         self.launches += 1
+        if chan_sums is not None and not out_nchw and P_out == 1 and out.dtype == torch.bfloat16:
+            o = out.double().reshape(N, -1, out.shape[-1])          # statistics of the values as stored
+            chan_sums[:, :, 0] += o.sum(1)
+            chan_sums[:, :, 1] += (o * o).sum(1)
+            return True
+        return None
 
     def wgrad(self, x0, x1, P_in, dy, P_dy, dw, N, H, W, k, dtype, in_nchw=False, dy_nchw=False, workspace=None, alg_frac=1.0):
         xin = self._logical_in(x0, x1, P_in, in_nchw)
@@ -114,6 +120,11 @@ class EmuOps:
         xh = (x.reshape(N, HW, G, C // G) - mean.float()[:, None, :, None]) * rstd.float()[:, None, :, None]
         z = xh.reshape(N, HW, C) * gamma.float() + beta.float()
         return _swish(z) if act else z
+
+    def gn_group_sums(self, cs0, cs1, N, G, sums):
+        cs = cs0 if cs1 is None else torch.cat([cs0, cs1], 1)
+        sums.copy_(cs.reshape(N, G, -1, 2).sum(2))
+        self.launches += 1
 
     def gn_apply(self, x0, x1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, out):
         assert p_drop == 0, "the test double does not model the counter-based dropout stream"

@@ -110,6 +110,30 @@ def test_conv_wgrad(case, mode):
     ops.use_tc = True
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[5] == 1], ids=[c[0] for c in CONV_CASES if c[5] == 1])
+def test_conv_epilogue_channel_statistics(case):
+    """hd_conv_tc's optional per-image per-channel (sum, sum of squares) of the stored output, and the group statistics
+    derived from them, against torch on the kernel's own bf16 output."""
+    name, C0, C1, P_in, Cout, P_out, N, H, W, k, use_emb, use_res = case
+    dev = torch.device("cuda")
+    ops = _ops()
+    x0, x1, w, bias, emb, res = _conv_inputs(case, torch.bfloat16, dev)
+    out = torch.empty(N, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    cs = torch.zeros(N, Cout, 2, dtype=torch.float64, device=dev)
+    got = ops.conv(x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, chan_sums=cs)
+    torch.cuda.synchronize()
+    assert got is True
+    o = out.double().reshape(N, H * W, Cout)
+    assert torch.allclose(cs[:, :, 0], o.sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(cs[:, :, 1], (o * o).sum(1), rtol=1e-5, atol=1e-3)
+    if Cout % 32 == 0:
+        sums = torch.empty(N, 32, 2, dtype=torch.float64, device=dev)
+        ops.gn_group_sums(cs, None, N, 32, sums)
+        ref = torch.empty_like(sums)
+        ops.gn_stats(out, None, N, H * W, 32, ref)
+        assert torch.allclose(sums, ref, rtol=1e-5, atol=1e-3)
+
+
 def test_head_tail_layout_convs():
     """3-channel NCHW fp32 boundary: head (NCHW fp32 -> NHWC) and tail (NHWC -> NCHW fp32), forward + wgrad."""
     dev = torch.device("cuda")
