@@ -44,8 +44,8 @@ constexpr int kHaloSlot = 9 * 1024;
 // channel chunk cc; all blocks with the same (ty, py, cc) read one halo box at pixel offset tx.
 struct GroupLayout {
     int nunits;
-    int u_cc[8], u_py[8], u_ty[8];            // per unit
-    int b_unit[8], b_tx[8];                   // per block
+    int u_cc[8], u_py[8], u_ty[8];            // per unit (at most 8 per stage)
+    int b_unit[16], b_tx[16];                 // per block (at most 2 x 8 groups)
 };
 __host__ __device__ inline void decode_group(const WgradTcParams& p, int group, GroupLayout* L) {
     L->nunits = 0;
@@ -171,11 +171,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
             const uint32_t idesc = umma_idesc_bf16(128, p.NT, 1, 1);
             int stage = 0; uint32_t phase = 0;
             // offset of the first block of each 128-row pair inside the A part of a stage, and the distance to its second block
-            uint32_t a_off[4], a_lbo[4];
+            uint32_t a_off[8], a_lbo[8];
             if (p.halo) {
                 GroupLayout L;
                 decode_group(p, group, &L);
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 8; ++g) {
                     if (g < p.G) {
                         const uint32_t o0 = L.b_unit[2 * g] * kHaloSlot + L.b_tx[2 * g] * 128;
                         const uint32_t o1 = L.b_unit[2 * g + 1] * kHaloSlot + L.b_tx[2 * g + 1] * 128;
@@ -183,7 +183,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
                     } else { a_off[g] = 0; a_lbo[g] = 0; }
                 }
             } else {
-                for (int g = 0; g < 4; ++g) { a_off[g] = g * 2 * kBlkBytes; a_lbo[g] = kBlkBytes; }
+                for (int g = 0; g < 8; ++g) { a_off[g] = g * 2 * kBlkBytes; a_lbo[g] = kBlkBytes; }
             }
             for (int s = 0; s < nsteps; ++s) {
                 mbar_wait(&full[stage], phase);
@@ -191,7 +191,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
                 const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t sb = sa + a_bytes;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 8; ++g) {
                     if (g >= p.G) break;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {    // K = 16 pixels = 2 groups of 8 rows = 2048 bytes
@@ -297,7 +297,7 @@ bool make_plan(int C0, int C1, int P_in, int Cdy, int P_dy, int N, int H, int W,
     if (!halo_off && k == 3 && p.TH == 1 && p.TW == 64) {
         // halo mode: the stage shrinks (one box per tap row instead of one per tap), so take the largest G (fewest groups)
         WgradTcParams q = p;
-        int Gh = 512 / p.NT; if (Gh > 4) Gh = 4; if (Gh > npairs) Gh = npairs;
+        int Gh = 512 / p.NT; if (Gh > 8) Gh = 8; if (Gh > npairs) Gh = npairs;     // up to 8 accumulators of NT columns
         while (Gh > 1 && (npairs + Gh - 2) / (Gh - 1) == (npairs + Gh - 1) / Gh) --Gh;
         q.G = Gh; q.ngroups = (npairs + Gh - 1) / Gh;
         bool ok = true; int max_units = 0;
