@@ -184,17 +184,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             // per-channel addend (bias + this image's embedding row) staged once per tile while the MMAs still run; the
             // element loop then reads it as shared-memory broadcasts instead of 32 dependent global loads per chunk
             float* add_t = addend + acc * 256;
-            {
-                const float* emb_row = p.emb ? p.emb + (long long)n * p.emb_stride : nullptr;
-                for (int c = etid; c < p.NT; c += 32 * kEpiWarps) {
-                    const int j = n_tile * p.NT + c;
-                    float a = p.bias ? __ldg(p.bias + j) : 0.f;
-                    if (emb_row) a += __ldg(emb_row + j);
-                    add_t[c] = a;
+            // NT <= 256 = number of epilogue threads: one addend element per thread.  The loads for the NEXT tile are
+            // issued here and only stored to shared memory after this tile's chunks, so their latency (a global round trip
+            // per tile, which used to sit in front of the barrier below) overlaps the chunk processing.
+            auto addend_load = [&](int tl) {
+                float a = 0.f;
+                if (etid < p.NT) {
+                    const int nt = tl % p.n_tiles, nn = (tl / p.n_tiles) / (p.tiles_x * p.tiles_y);
+                    const int j = nt * p.NT + etid;
+                    if (p.bias) a = __ldg(p.bias + j);
+                    if (p.emb) a += __ldg(p.emb + (long long)nn * p.emb_stride + j);
                 }
-                if (kStats) for (int c = etid; c < 2 * p.NT; c += 32 * kEpiWarps) stat_s[acc * 512 + c] = 0.f;
-                asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps only
-            }
+                return a;
+            };
+            if (it == 0 && etid < p.NT) add_t[etid] = addend_load(tile);
+            const bool has_next = tile + (int)gridDim.x < total_tiles;
+            float a_next = 0.f;
+            if (has_next) a_next = addend_load(tile + gridDim.x);
+            if (kStats) for (int c = etid; c < 2 * p.NT; c += 32 * kEpiWarps) stat_s[acc * 512 + c] = 0.f;
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps only: this tile's addend is staged
             // element offset of this thread's pixel for output-channel 0 of each parity (P_out == 2 stores the four
             // parities of the transposed convolution through the 2x2 view); hoisted out of the chunk loop
             const long long pix1 = (((long long)n * p.H + y) * p.W + x) * p.Cout;
@@ -297,6 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (has_next && etid < p.NT) addend[(acc ^ 1) * 256 + etid] = a_next;     // visible after the next iteration's barrier
             if (kStats) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");          // every warp's contribution to this tile is in shared memory
                 for (int c = etid; c < 2 * p.NT; c += 32 * kEpiWarps)
