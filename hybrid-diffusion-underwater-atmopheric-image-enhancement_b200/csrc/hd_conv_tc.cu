@@ -45,8 +45,8 @@ struct ConvTcParams {
                                      // the parity wait on `empty` cannot tell 0 completed phases from 2)
 };
 
-template <bool kStats>     // kStats: the epilogue also accumulates p.chan_sums (separate instantiation: the extra registers and
-                           // shuffles must not slow the plain epilogue down)
+template <bool kStats, bool kRes>   // kStats: the epilogue also accumulates p.chan_sums; kRes: a residual tensor is added (its loads are
+                                    // prefetched).  Separate instantiations: the extra registers must not slow the plain epilogue down
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const ConvTcParams p) {
@@ -208,6 +208,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const long long pix1 = (((long long)n * p.H + y) * p.W + x) * p.Cout;
             const long long pix2 = (((long long)n * (2 * p.H) + 2 * y) * (2 * p.W) + 2 * x) * p.Cout;
             const long long q_dx = p.Cout, q_dy = 2ll * p.W * p.Cout;
+            uint4 pre_a[2], pre_b[2];
+            const bool have_pre = kRes && valid && !p.out_nchw && half * 16 < p.NT;
+            if (have_pre) {
+                const int c0 = half * 16;
+                long long o;
+                {
+                    const int j = n_tile * p.NT + c0;
+                    if (p.P_out == 1) o = pix1 + j;
+                    else { const int q = j / p.Cout, cph = j - q * p.Cout; o = pix2 + (q >> 1) * q_dy + (q & 1) * q_dx + cph; }
+                }
+                const uint4* rp = reinterpret_cast<const uint4*>(p.res + o);
+                pre_a[0] = __ldg(rp); pre_a[1] = __ldg(rp + 1);
+                if (c0 + 32 < p.NT) {
+                    const int j = n_tile * p.NT + c0 + 32;
+                    if (p.P_out == 1) o = pix1 + j;
+                    else { const int q = j / p.Cout, cph = j - q * p.Cout; o = pix2 + (q >> 1) * q_dy + (q & 1) * q_dx + cph; }
+                    const uint4* rq = reinterpret_cast<const uint4*>(p.res + o);
+                    pre_b[0] = __ldg(rq); pre_b[1] = __ldg(rq + 1);
+                }
+            }
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
@@ -227,7 +247,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 }
             } else {
-                auto emit = [&](const uint32_t* v, int c, float* f) {
+                // residual of the first chunk pair of this warp, requested BEFORE the accumulator is awaited (it does not depend
+                // on the MMAs): for NT <= 64 that is every residual load of the tile
+                auto emit = [&](const uint32_t* v, int c, float* f, const uint4* pre) {
                     const int j = n_tile * p.NT + c;            // logical output channel of v[0]
                     long long off;
                     if (p.P_out == 1) {
@@ -243,9 +265,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         f[4 * i] = __uint_as_float(v[4 * i]) + a.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + a.y;
                         f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + a.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + a.w;
                     }
-                    if (p.res) {
+                    if (kRes) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
-                        uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                        uint4 r0, r1;
+                        if (pre) { r0 = pre[0]; r1 = pre[1]; } else { r0 = __ldg(rp); r1 = __ldg(rp + 1); }
                         const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
                         const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
 #pragma unroll
@@ -288,13 +311,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 for (int c = half * 16; c < p.NT; c += 64) {
                     uint32_t va[16], vb[16];
                     const bool two = c + 32 < p.NT;
+                    const bool first = c == half * 16;
                     tmem_ld16(taddr + c, va);
                     if (two) tmem_ld16(taddr + c + 32, vb);
                     tmem_wait_ld();
                     float fa[16], fb[16];
                     if (valid) {
-                        emit(va, c, fa);
-                        if (two) emit(vb, c + 32, fb);
+                        emit(va, c, fa, first && have_pre ? pre_a : nullptr);
+                        if (two) emit(vb, c + 32, fb, first && have_pre ? pre_b : nullptr);
                     }
                     if (kStats) {
                         stats(fa, valid, c);
@@ -442,15 +466,22 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 2 * 256 * 4 + 2 * 512 * 4;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             hd_set_error("cudaFuncSetAttribute(conv_tc_kernel)"); return HD_ERR_CUDA;
         }
         attr_set = true;
     }
     int grid = p.m_tiles * p.n_tiles; const int sms = hd_num_sms(); if (grid > sms) grid = sms;
-    if (chan_sums) conv_tc_kernel<true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
-    else conv_tc_kernel<false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
+    if (chan_sums) {
+        if (res) conv_tc_kernel<true, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
+        else conv_tc_kernel<true, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
+    } else {
+        if (res) conv_tc_kernel<false, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
+        else conv_tc_kernel<false, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
+    }
     HD_CHECK_LAUNCH();
     return HD_OK;
 }

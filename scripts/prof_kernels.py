@@ -44,6 +44,10 @@ if what in ("conv", "wgrad", "all"):
         if what in ("conv", "all"):
             timeit(f"conv{k}x{k} N{N} {H}x{W} {C0}+{C1}->{Cout}", lambda: ops.conv(x0, x1, 1, w, bias, None, None, out, 1, N, H, W, k), fl / 1e3, "TFLOP/s")
         if what in ("conv", "all") and k == 3:
+            res_t = torch.randn(N, H, W, Cout, device=dev).to(bf)
+            emb_t = torch.randn(N, Cout, device=dev)
+            timeit(f"conv{k}x{k}+res+emb N{N} {H}x{W} {C0}+{C1}->{Cout}", lambda: ops.conv(x0, x1, 1, w, bias, emb_t, res_t, out, 1, N, H, W, k), fl / 1e3, "TFLOP/s")
+        if what in ("conv", "all") and k == 3 and False:
             cs = torch.zeros(N, Cout, 2, dtype=torch.float64, device=dev)
             timeit(f"conv{k}x{k}+stats N{N} {H}x{W} {C0}+{C1}->{Cout}", lambda: ops.conv(x0, x1, 1, w, bias, None, None, out, 1, N, H, W, k, chan_sums=cs), fl / 1e3, "TFLOP/s")
         if what in ("wgrad", "all"):
