@@ -319,9 +319,11 @@ bool make_plan(int C0, int C1, int P_in, int Cdy, int P_dy, int N, int H, int W,
     }
     p.stages = (200 * 1024) / stage_bytes; if (p.stages > kMaxStages) p.stages = kMaxStages;
     if (p.stages < 2) return false;
-    // split-K over pixel tiles: fill the machine about twice
+    // split-K over pixel tiles: one CTA per SM (a CTA owns all 512 TMEM columns, so more CTAs would only queue up), i.e. one
+    // wave of equal-length CTAs and half the fp32 partials of a two-wave split
     const int ctas_per_split = p.ngroups * p.n_tiles;
-    int splits = (2 * 148 + ctas_per_split - 1) / ctas_per_split;
+    static const int waves = getenv("HDIFF_WGRAD_WAVES") ? atoi(getenv("HDIFF_WGRAD_WAVES")) : 1;
+    int splits = (waves * hd_num_sms()) / ctas_per_split;          // floor: never spill a few CTAs into another wave
     if (splits > p.pix_tiles) splits = p.pix_tiles;
     if (splits < 1) splits = 1;
     p.tiles_per_split = (p.pix_tiles + splits - 1) / splits;
