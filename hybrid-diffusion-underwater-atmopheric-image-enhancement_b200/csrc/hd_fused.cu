@@ -111,8 +111,10 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(Src2<T> x, int N, int64_t
     }
 }
 
-static inline int64_t pick_chunk(int N, int64_t HW, int ppi, int* chunks_out) {
-    int64_t target_blocks = (int64_t)hd_num_sms() * 8;
+// blocks_per_sm x waves: the grid is sized to whole waves of resident blocks (a kernel that keeps 3 blocks per SM resident and
+// is launched with 8 blocks per SM runs 2.67 waves: the last one is two-thirds empty)
+static inline int64_t pick_chunk(int N, int64_t HW, int ppi, int* chunks_out, int blocks_per_sm = 8) {
+    int64_t target_blocks = (int64_t)hd_num_sms() * blocks_per_sm;
     int64_t chunks = (target_blocks + N - 1) / N;
     int64_t max_chunks = (HW + ppi - 1) / ppi;
     if (chunks > max_chunks) chunks = max_chunks;
@@ -224,7 +226,9 @@ template <typename T>
 static int gn_apply_t(const void* in0, int C0, const void* in1, int C1, GnParams g, void* out, cudaStream_t st) {
     int rc = gn_check<T>(C0, C1, g.G); if (rc) return rc;
     int ppi = 256 / (g.C / Vec<T>::N), chunks;
-    int64_t ppb = pick_chunk(g.N, g.HW, ppi, &chunks);
+    static int per_sm = 0;
+    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_apply_kernel<T>, 256, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;
+    int64_t ppb = pick_chunk(g.N, g.HW, ppi, &chunks, 3 * per_sm);
     gn_apply_kernel<T><<<dim3((unsigned)chunks, g.N), 256, 0, st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, ppb, (T*)out);
     HD_CHECK_LAUNCH();
     return HD_OK;
