@@ -229,3 +229,52 @@ def test_odd_resolution_uses_the_generic_kernels_correctly():
         if pr[k].grad is None:
             continue
         assert _close(p.grad, pr[k].grad, 0.12, 6e-3 * 3e-2 * gscale + 2e-5), (k, _rel(p.grad, pr[k].grad))
+
+
+def test_sampler_cuda_graph_matches_eager():
+    """The ancestral step replayed as a CUDA graph (device-side time index) gives the same chain as eager launches: same
+    RNG stream, same kernels.  Short chain so that rounding-order differences of the fp64 GroupNorm atomics stay small."""
+    from hdiff_b200.DiffusionFreeGuidence.DiffusionCondition import GaussianDiffusionSampler
+    dev = torch.device("cuda")
+    cfg = dict(T=1000, ch=64, ch_mult=[1, 2], attn=[1], num_res_blocks=1, dropout=0.0)
+    net, _ = _nets(cfg, 10, torch.bfloat16, dev, seed=61)
+    net.eval()
+    xT = torch.randn(2, 3, 32, 32, device=dev)
+    lab = torch.tensor([3, 8], device=dev)
+    outs = []
+    for graph in (True, False):
+        smp = GaussianDiffusionSampler(net, 1e-4, 0.02, 12, w=1.8).to(dev)
+        smp.use_cuda_graph = graph
+        torch.manual_seed(62)
+        outs.append(smp(xT, lab))
+    assert float((outs[0] - outs[1]).abs().max()) < 2e-2
+    assert float(outs[0].abs().max()) <= 1.0
+
+
+def test_flat_adamw_matches_clip_grad_norm_plus_torch_adamw():
+    """hdiff_b200.optim.FlatAdamW (global-norm clip + AdamW in two launches over the flat buffers) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW on the same gradients, three steps."""
+    from hdiff_b200.optim import FlatAdamW
+    dev = torch.device("cuda")
+    cfg = dict(T=100, ch=64, ch_mult=[1, 2], attn=[1], num_res_blocks=1, dropout=0.0)
+    a, _ = _nets(cfg, None, torch.bfloat16, dev, seed=71)
+    b, _ = _nets(cfg, None, torch.bfloat16, dev, seed=71)
+    oa = FlatAdamW(a, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0)
+    ob = torch.optim.AdamW([p for p in b.parameters()], lr=1e-3, weight_decay=1e-2)
+    torch.manual_seed(72)
+    x = torch.rand(2, 3, 32, 32, device=dev) * 2 - 1
+    t = torch.tensor([5, 50], device=dev)
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    for _ in range(3):
+        oa.zero_grad(); ob.zero_grad()
+        (a(x, t) ** 2).sum().backward()
+        for k in pa:                                  # the SAME gradients for both optimisers (Adam normalises: gradient noise
+            if pa[k].grad is not None:                # of two separate backward passes would flip near-zero updates)
+                pb[k].grad = pa[k].grad.detach().clone()
+        oa.step()
+        torch.nn.utils.clip_grad_norm_([p for p in b.parameters() if p.grad is not None], 1.0)
+        ob.step()
+    for k in pa:
+        if k.endswith("cond_proj.1.weight") or k.endswith("cond_proj.1.bias"):
+            continue            # never used by the unconditional model: torch skips them (grad None), the flat step only decays them
+        assert torch.allclose(pa[k].detach(), pb[k].detach(), rtol=1e-4, atol=2e-6), (k, float((pa[k] - pb[k]).abs().max()))
