@@ -47,9 +47,12 @@ PROTOTYPES = {
     "hd_attn_fwd_tc": [P, P, P, I, I, I, P],
     "hd_attn_bwd_tc": [P, P, P, P, P, P, I, I, I, P],
     "hd_attn_tc_supported": [I, I],
+    "hd_attn_wide_tc_supported": [I, I],
+    "hd_attn_fwd_wide_tc": [P, P, P, I, I, I, P],
+    "hd_attn_bwd_wide_tc": [P, P, P, P, P, P, I, I, I, P],
     "hd_attn_bwd_tc_supported": [I, I],
 }
-NON_STATUS = {"hd_conv_tc_supported", "hd_wgrad_tc_supported", "hd_attn_tc_supported", "hd_attn_bwd_tc_supported",
+NON_STATUS = {"hd_conv_tc_supported", "hd_wgrad_tc_supported", "hd_attn_tc_supported", "hd_attn_bwd_tc_supported", "hd_attn_wide_tc_supported",
               "hd_wgrad_tc_workspace"}
 
 _lib = None

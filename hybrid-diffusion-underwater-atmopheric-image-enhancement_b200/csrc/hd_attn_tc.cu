@@ -683,12 +683,22 @@ __global__ void attn_stats_kernel(const __nv_bfloat16* o, const __nv_bfloat16* d
 
 }  // namespace
 
-extern "C" int hd_attn_tc_supported(int S, int C) { return (C == D && S >= BM && S % BM == 0) ? 1 : 0; }
+// wide heads (C = 256, 384, ...): hd_attn_wide_tc.cu
+extern "C" int hd_attn_wide_tc_supported(int S, int C);
+extern "C" int hd_attn_fwd_wide_tc(const void* qkv, void* out, float* lse, int N, int S, int C, cudaStream_t stream);
+extern "C" int hd_attn_bwd_wide_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* stats, void* dqkv,
+                                   int N, int S, int C, cudaStream_t stream);
+
+extern "C" int hd_attn_tc_supported(int S, int C) {
+    if (C != D) return hd_attn_wide_tc_supported(S, C);
+    return (S >= BM && S % BM == 0) ? 1 : 0;
+}
 extern "C" int hd_attn_bwd_tc_supported(int S, int C) { return hd_attn_tc_supported(S, C); }
 
 extern "C" int hd_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int S, int C, cudaStream_t stream) {
     HD_REQUIRE(qkv && out && lse && N > 0);
     if (!hd_attn_tc_supported(S, C)) { hd_set_error("hd_attn_fwd_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
+    if (C != D) return hd_attn_fwd_wide_tc(qkv, out, lse, N, S, C, stream);
     CUtensorMap m;
     int rc = make_qkv_map(&m, qkv, N, S, 3 * C, 64); if (rc) return rc;
     AttnFwdParams p{};
@@ -723,6 +733,7 @@ extern "C" int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout
                               int N, int S, int C, cudaStream_t stream) {
     HD_REQUIRE(qkv && out && dout && lse && stats && dqkv && N > 0);
     if (!hd_attn_bwd_tc_supported(S, C)) { hd_set_error("hd_attn_bwd_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
+    if (C != D) return hd_attn_bwd_wide_tc(qkv, out, dout, lse, stats, dqkv, N, S, C, stream);
     CUtensorMap mQKV, mDO;
     int rc = make_qkv_map(&mQKV, qkv, N, S, 3 * C, 64); if (rc) return rc;
     rc = make_qkv_map(&mDO, dout, N, S, C, 64); if (rc) return rc;

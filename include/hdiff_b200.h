@@ -70,6 +70,12 @@ int hd_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int S, int C, 
  * atomics; `stats` is caller-provided scratch of N*S*2 floats ((lse*log2e, rowsum(dout*out)) per row). */
 int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* stats, void* dqkv,
                    int N, int S, int C, hd_stream_t stream);
+/* Wide heads (C a multiple of 128 up to 1024; hd_attn_*_tc forward to these when C != 128): the AttnBlocks of the wider
+ * UNet of BASELINE.json configs[4] (C = 256 at 64x64, C = 512 at 32x32).  Same arguments and semantics as above. */
+int hd_attn_wide_tc_supported(int S, int C);
+int hd_attn_fwd_wide_tc(const void* qkv, void* out, float* lse, int N, int S, int C, hd_stream_t stream);
+int hd_attn_bwd_wide_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* stats, void* dqkv,
+                        int N, int S, int C, hd_stream_t stream);
 
 /* ---- GroupNorm(32) + Swish (+ Dropout): ModelCondition.py:128-129,141-143,95,249-250.  Two-source input
  *      (C0 | C1 channels) fuses torch.cat :271 into the normalisation.  sums/gsums = [N][G][2] fp64. ---- */

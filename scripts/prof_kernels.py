@@ -69,6 +69,16 @@ if what in ("attn", "attn32", "all"):
         timeit(f"attn fwd N{N} S{S}", lambda: ops.attn_fwd(qkv, out, lse, N, S, C), 4.0 * N * S * S * C / 1e3, "TFLOP/s")
         timeit(f"attn bwd N{N} S{S}", lambda: ops.attn_bwd(qkv, out, dout, lse, None, dqkv, N, S, C), 8.0 * N * S * S * C / 1e3, "TFLOP/s")
 
+if what in ("attnwide",):
+    for N, S, C in ((4, 4096, 256), (4, 1024, 512), (32, 4096, 256), (8, 4096, 128)):
+        qkv = torch.randn(N, S, 3 * C, device=dev).to(bf)
+        out = torch.empty(N, S, C, dtype=bf, device=dev)
+        dout = torch.randn(N, S, C, device=dev).to(bf)
+        dqkv = torch.empty_like(qkv)
+        lse = torch.empty(N, S, device=dev)
+        timeit(f"attn fwd N{N} S{S} C{C}", lambda: ops.attn_fwd(qkv, out, lse, N, S, C), 4.0 * N * S * S * C / 1e3, "TFLOP/s")
+        timeit(f"attn bwd N{N} S{S} C{C}", lambda: ops.attn_bwd(qkv, out, dout, lse, None, dqkv, N, S, C), 8.0 * N * S * S * C / 1e3, "TFLOP/s")
+
 if what in ("gn", "all"):
     for (N, HW, C0, C1, p_drop) in ((32, 65536, 64, 0, 0.0), (32, 65536, 64, 0, 0.1), (32, 16384, 128, 0, 0.1), (32, 65536, 128, 64, 0.0)):
         C = C0 + C1

@@ -304,6 +304,48 @@ def test_attention_tcgen05_backward(S, N, qscale):
         assert r < 1.5e-2, (name, r)
 
 
+@pytest.mark.parametrize("S,N,C,qscale", [(256, 2, 256, 1.0), (1024, 2, 256, 1.0), (4096, 1, 256, 1.0), (1024, 2, 512, 1.0), (256, 1, 384, 1.0),
+                                          (1024, 2, 256, 8.0), (512, 3, 128, 1.0), (1024, 1, 1024, 1.0)])
+def test_attention_tcgen05_wide_heads(S, N, C, qscale):
+    """Wide-head tcgen05 attention (hd_attn_wide_tc.cu: C = 256 / 512 levels of BASELINE.json configs[4]) forward and backward
+    against the fp32 formula.  C = 128 goes through the wide entry points directly (the dispatcher keeps C = 128 on the
+    dedicated kernels)."""
+    import ctypes
+    dev = torch.device("cuda")
+    ops, emu = _ops(), EmuOps()
+    assert ops.lib.hd_attn_wide_tc_supported(S, C) and ops.lib.hd_attn_tc_supported(S, C) and ops.lib.hd_attn_bwd_tc_supported(S, C)
+    torch.manual_seed(11 * S + C + int(qscale))
+    qkv = torch.randn(N, S, 3 * C, device=dev)
+    qkv[:, :, :C] *= qscale
+    qkv[:, :, C:2 * C] *= torch.linspace(0.5, 1.5, S, device=dev)[None, :, None]
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.full((N, S, C), float("nan"), dtype=torch.bfloat16, device=dev)
+    lse = torch.full((N, S), float("nan"), device=dev)
+    dout = torch.randn(N, S, C, device=dev).to(torch.bfloat16)
+    dqkv = torch.full_like(qkv, float("nan"))
+    if C == 128:
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stats = torch.empty(N, S, 2, device=dev)
+        assert ops.lib.hd_attn_fwd_wide_tc(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), N, S, C, st) == 0
+        assert ops.lib.hd_attn_bwd_wide_tc(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), stats.data_ptr(),
+                                           dqkv.data_ptr(), N, S, C, st) == 0
+    else:
+        before = ops.tc_launches
+        ops.attn_fwd(qkv, out, lse, N, S, C)
+        ops.attn_bwd(qkv, out, dout, lse, None, dqkv, N, S, C)
+        assert ops.tc_launches == before + 3
+    torch.cuda.synchronize()
+    ro, rl = torch.empty(N, S, C, device=dev), torch.empty(N, S, device=dev)
+    emu.attn_fwd(qkv.float(), ro, rl, N, S, C)
+    assert _rel(out.float(), ro) < 1e-2, _rel(out.float(), ro)
+    assert float((lse - rl).abs().max()) < 2e-2 * max(1.0, float(rl.abs().max()) * 0.05), float((lse - rl).abs().max())
+    rd = torch.empty(N, S, 3 * C, device=dev)
+    emu.attn_bwd(qkv.float(), None, dout.float(), None, None, rd, N, S, C)
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        r = _rel(dqkv[:, :, sl].float(), rd[:, :, sl])
+        assert r < 1.5e-2, (name, r)
+
+
 def test_embedding_path_and_packing_kernels():
     dev = torch.device("cuda")
     ops, emu = _ops(), EmuOps()
