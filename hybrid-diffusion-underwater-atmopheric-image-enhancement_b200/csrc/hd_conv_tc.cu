@@ -41,6 +41,10 @@ struct ConvTcParams {
     int a_slot, a_tx;                // shared-memory bytes reserved for / transferred into the A part of a stage
     double* chan_sums;               // optional [N][Cout][2]: per-image, per-channel sum / sum of squares of the STORED output
                                      // (the GroupNorm statistics of the next layer, without another pass over the tensor)
+    int stage_out;                   // epilogue stages 64-channel blocks of the tile in shared memory (128-byte swizzle) and writes them
+                                     // with TMA tensor stores: whole 128-byte lines instead of 32-byte pieces per thread
+    int wres, kb_w;                  // wres: the whole packed weight matrix (n_tiles x kb_w blocks of [NT][64] bf16) is loaded ONCE per CTA
+                                     // and stays in shared memory; the ring then carries activations only
     int nprod;                       // issuing threads in use (<= stages: a producer must never be two ring laps ahead,
                                      // the parity wait on `empty` cannot tell 0 completed phases from 2)
 };
@@ -49,26 +53,31 @@ template <bool kStats, bool kRes>   // kStats: the epilogue also accumulates p.c
                                     // prefetched).  Separate instantiations: the extra registers must not slow the plain epilogue down
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               const __grid_constant__ CUtensorMap mapB, const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut, const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = p.NT * 128;
-    const int stage_bytes = p.a_slot + (p.txm ? 3 : 1) * b_bytes;
-    const int stage_tx = p.a_tx + (p.txm ? 3 : 1) * b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    const int stage_bytes = p.a_slot + (p.wres ? 0 : (p.txm ? 3 : 1) * b_bytes);
+    const int stage_tx = p.a_tx + (p.wres ? 0 : (p.txm ? 3 : 1) * b_bytes);
+    uint8_t* stage_buf = smem + (size_t)p.stages * stage_bytes;                  // [2][128 pixels][64 channels] bf16 when p.stage_out
+    uint8_t* wres_buf = stage_buf + (p.stage_out ? 2 * kABytes : 0);             // [n_tiles][kb_w][NT][64] bf16 when p.wres
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wres_buf + (p.wres ? (size_t)p.n_tiles * p.kb_w * b_bytes : 0));
     uint64_t* full = bars;                       // [stages]
     uint64_t* empty = bars + kMaxStages;         // [stages]
     uint64_t* tfull = bars + 2 * kMaxStages;     // [2]
     uint64_t* tempty = bars + 2 * kMaxStages + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    uint64_t* wfull = bars + 2 * kMaxStages + 5;   // resident weights have landed
     float* addend = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);     // [2][256]: bias + embedding row of a tile
     float* stat_s = addend + 2 * 256;                                        // [2][256][2]: per-tile channel sums (p.chan_sums)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB);
+        if (p.stage_out) tma_prefetch_desc(&mapOut);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
+        mbar_init(wfull, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -83,6 +92,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             int turn = 0;                                // global K-block counter modulo kProducers
+            if (p.wres && prod == 0) {
+                mbar_arrive_expect_tx(wfull, (uint32_t)(p.n_tiles * p.kb_w * b_bytes));
+                for (int nt = 0; nt < p.n_tiles; ++nt)
+                    for (int kb = 0; kb < p.kb_w; ++kb)
+                        tma_load_2d(wres_buf + (size_t)(nt * p.kb_w + kb) * b_bytes, &mapB, wfull, kb * 64, nt * p.NT);
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
                 const int tx_i = m_tile % p.tiles_x; const int r = m_tile / p.tiles_x;
@@ -106,8 +121,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                     if (cc < p.nchunk0) tma_load_5d(sa, &mapA0, &full[stage], cc * 64, x0 - 1, py, y0 + ty - 1, n);
                                     else tma_load_5d(sa, &mapA1, &full[stage], (cc - p.nchunk0) * 64, x0 - 1, py, y0 + ty - 1, n);
                                     const int kb0 = (ty * 3 * p.P_in + py) * p.nchunk_c + cc;
-                                    for (int tx = 0; tx < 3; ++tx)
-                                        tma_load_2d(sa + p.a_slot + tx * b_bytes, &mapB, &full[stage], (kb0 + tx * tap_stride) * 64, n_tile * p.NT);
+                                    if (!p.wres)
+                                        for (int tx = 0; tx < 3; ++tx)
+                                            tma_load_2d(sa + p.a_slot + tx * b_bytes, &mapB, &full[stage], (kb0 + tx * tap_stride) * 64, n_tile * p.NT);
                                 }
                                 if (++turn == p.nprod) turn = 0;
                                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -125,7 +141,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                                     if (cc < p.nchunk0) tma_load_5d(sa, &mapA0, &full[stage], cc * 64, x0 + tx - p.pad, py, y0 + ty - p.pad, n);
                                     else tma_load_5d(sa, &mapA1, &full[stage], (cc - p.nchunk0) * 64, x0 + tx - p.pad, py, y0 + ty - p.pad, n);
-                                    tma_load_2d(sa + p.a_slot, &mapB, &full[stage], kb * 64, n_tile * p.NT);
+                                    if (!p.wres) tma_load_2d(sa + p.a_slot, &mapB, &full[stage], kb * 64, n_tile * p.NT);
                                 }
                                 if (++turn == p.nprod) turn = 0;
                                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -136,11 +152,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
             int stage = 0; uint32_t phase = 0; int it = 0;
+            if (p.wres) { mbar_wait(wfull, 0); tc_fence_after(); }
+            const int per_row = p.P_in * p.nchunk_c;     // txm: stages per tap row = K blocks between two tap columns
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
+                const uint32_t wb = smem_u32(wres_buf) + (uint32_t)((tile % p.n_tiles) * p.kb_w * b_bytes);
+                int kb0 = 0, in_row = 0;                 // txm + resident weights: first K block (tap column 0) of this stage
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
@@ -149,14 +169,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
                         for (int tx = 0; tx < 3; ++tx) {
                             const uint64_t adesc = umma_smem_desc(sa + tx * 128, 16, 1024);      // halo box, shifted by tx pixels
-                            const uint64_t bdesc = umma_smem_desc(sa + p.a_slot + tx * b_bytes, 16, 1024);
+                            const uint64_t bdesc = umma_smem_desc(p.wres ? wb + (uint32_t)((kb0 + tx * per_row) * b_bytes)
+                                                                         : sa + p.a_slot + tx * b_bytes, 16, 1024);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tx | k) != 0);
                         }
+                        ++kb0;
+                        if (++in_row == per_row) { in_row = 0; kb0 += 2 * per_row; }
                     } else {
                     const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
-                    const uint64_t bdesc = umma_smem_desc(sa + p.a_slot, 16, 1024);
+                    const uint64_t bdesc = umma_smem_desc(p.wres ? wb + (uint32_t)(kb * b_bytes) : sa + p.a_slot, 16, 1024);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // 4 x (K = 16): advance 32 bytes inside the 128-byte swizzle atom
                         umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
@@ -174,6 +197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int etid = (warp - 2) * 32 + lane;     // 0 .. 255 among the epilogue threads
         const int ty = row / p.TW, tx = row % p.TW;
         int it = 0;
+        uint32_t sb = 0;                             // staged 64-channel blocks so far (p.stage_out): buffer = sb & 1
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
@@ -245,6 +269,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             }
                         }
                     }
+                }
+            } else if (p.stage_out) {
+                // One loop iteration of the eight warps completes a [128 pixels][64 channels] block (this warp: the 16-column
+                // chunks half*16 and half*16 + 32 of its 32 pixels).  Buffer protocol, one barrier per block: the issuing thread
+                // waits until every earlier store has been READ out of shared memory before it joins the barrier of block sb, so
+                // after that barrier the other buffer (store sb-1) is free for block sb+1, and buffer sb&1 is complete.
+                auto stage_emit = [&](const uint32_t* v, int c, uint8_t* srow, int cb, const uint4* pre) {
+                    const float4* a4 = reinterpret_cast<const float4*>(add_t + c);
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a = a4[i];
+                        f[4 * i] = __uint_as_float(v[4 * i]) + a.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + a.y;
+                        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + a.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + a.w;
+                    }
+                    if (kRes) {
+                        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+                        if (pre) { r0 = pre[0]; r1 = pre[1]; }
+                        else if (valid) {
+                            const int j = n_tile * p.NT + c;
+                            long long off;
+                            if (p.P_out == 1) off = pix1 + j;
+                            else { const int q = j / p.Cout, cph = j - q * p.Cout; off = pix2 + (q >> 1) * q_dy + (q & 1) * q_dx + cph; }
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
+                            r0 = __ldg(rp); r1 = __ldg(rp + 1);
+                        }
+                        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+                        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float2 a = __bfloat1622float2(h0[i]), b = __bfloat1622float2(h1[i]);
+                            f[2 * i] += a.x; f[2 * i + 1] += a.y; f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
+                        }
+                    }
+                    uint4 o0, o1;
+                    o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+                    o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                    *reinterpret_cast<uint4*>(srow + ((cb ^ (row & 7)) << 4)) = o0;             // 128-byte swizzle: chunk ^= row % 8
+                    *reinterpret_cast<uint4*>(srow + (((cb + 1) ^ (row & 7)) << 4)) = o1;
+                };
+                for (int c = half * 16; c < p.NT; c += 64) {
+                    uint32_t va[16], vb[16];
+                    const bool first = c == half * 16;
+                    tmem_ld16(taddr + c, va);
+                    tmem_ld16(taddr + c + 32, vb);
+                    tmem_wait_ld();
+                    uint8_t* sbuf = stage_buf + (sb & 1) * kABytes;
+                    stage_emit(va, c, sbuf + row * 128, half * 2, first && have_pre ? pre_a : nullptr);
+                    stage_emit(vb, c + 32, sbuf + row * 128, half * 2 + 4, first && have_pre ? pre_b : nullptr);
+                    fence_proxy_async_smem();
+                    if (etid == 0) bulk_wait_group_read0();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (etid == 0) {
+                        // logical channel block j0 of the tile -> (channel, parity row) of the output view (P_out == 2: the four
+                        // parities of a transposed convolution are channel ranges q * Cout, q = 2 py + px)
+                        const int j0 = n_tile * p.NT + (c - half * 16);
+                        const int cv_w = p.P_out * p.Cout;
+                        const int py = j0 / cv_w;
+                        tma_store_5d(&mapOut, sbuf, j0 - py * cv_w, tx_i * p.TW, py, ty_i * p.TH, n);
+                        bulk_commit_group();
+                    }
+                    ++sb;
                 }
             } else {
                 // residual of the first chunk pair of this warp, requested BEFORE the accumulator is awaited (it does not depend
@@ -336,6 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     atomicAdd(p.chan_sums + ((long long)n * p.Cout + n_tile * p.NT) * 2 + c, (double)stat_s[acc * 512 + c]);
             }
         }
+        if (p.stage_out && etid == 0) bulk_wait_group0();           // shared memory must outlive the last tensor store
     }
     tc_fence_before();
     __syncthreads();
@@ -432,18 +519,39 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     else { p.nchunk0 = 2 * C0 / 64; p.nchunk_c = p.nchunk0; }
     p.kblocks = ksize * ksize * P_in * p.nchunk_c;
     const int CinL = (C0 + C1) * P_in * P_in;
-    p.txm = 0; p.a_slot = kABytes; p.a_tx = kABytes;
-    int stage_bytes = kABytes + p.NT * 128;
-    {   // shifted-operand mode: 3x3, a tile is one 128-pixel row segment, and at least 3 stages fit
+    p.kb_w = p.kblocks;
+    {   // Shared-memory plan.  Options, each dropped when the ring would get too short:
+        //   txm   shifted-operand mode: 3x3, a tile is one 128-pixel row segment (needs >= 3 stages)
+        //   wres  resident weights: the packed weight matrix fits in 96 KB
+        //   stage staged tensor-store epilogue (2 x 16 KB)
         static const bool txm_off = getenv("HDIFF_CONV_TXM_OFF") != nullptr;
-        const int a_tx = (p.TW + 2) * 128, a_slot = (a_tx + 1023) / 1024 * 1024;
-        const int sb = a_slot + 3 * p.NT * 128;
-        if (!txm_off && ksize == 3 && p.TH == 1 && p.TW == 128 && (200 * 1024) / sb >= 3) {
-            p.txm = 1; p.a_slot = a_slot; p.a_tx = a_tx; stage_bytes = sb;
-            p.kblocks = 3 * P_in * p.nchunk_c;            // stages per tile: one per (tap row, parity row, chunk)
-        }
+        static const bool wres_on = getenv("HDIFF_CONV_WRES") != nullptr;    // measured: no gain (the operand fetch of the MMAs bounds
+                                                                             // the kernel, not the TMA fill), so off by default
+        static const int stage_env = getenv("HDIFF_CONV_STAGE") ? atoi(getenv("HDIFF_CONV_STAGE")) : 2;   // 0 off, 1 1x1 only, 2 every eligible conv
+        const int budget = 200 * 1024;
+        const long long wbytes = (long long)CoutL * p.kb_w * 128;
+        const bool want_txm = !txm_off && ksize == 3 && p.TH == 1 && p.TW == 128;
+        const bool want_wres = wres_on && wbytes <= 96 * 1024;
+        const bool want_stage = out_nchw_c == 0 && !chan_sums && p.NT % 64 == 0 && Cout % 64 == 0 &&
+                                (stage_env == 2 || (stage_env == 1 && ksize == 1));
+        const int txm_a_tx = (p.TW + 2) * 128, txm_a_slot = (txm_a_tx + 1023) / 1024 * 1024;
+        auto stages_of = [&](bool txm, bool wres, bool stage) {
+            const int sbytes = (txm ? txm_a_slot : kABytes) + (wres ? 0 : (txm ? 3 : 1) * p.NT * 128);
+            const long long avail = budget - (stage ? 2 * kABytes : 0) - (wres ? wbytes : 0);
+            return avail <= 0 ? 0 : (int)(avail / sbytes);
+        };
+        bool txm = false, wres = false, stage = false, found = false;
+        for (int t = want_txm ? 1 : 0; t >= 0 && !found; --t)
+            for (int w = want_wres ? 1 : 0; w >= 0 && !found; --w)
+                for (int g = want_stage ? 1 : 0; g >= 0 && !found; --g)
+                    if (stages_of(t, w, g) >= (t ? 3 : 2)) { txm = t; wres = w; stage = g; found = true; }
+        HD_REQUIRE(found);
+        p.txm = txm; p.wres = wres; p.stage_out = stage;
+        p.a_slot = txm ? txm_a_slot : kABytes; p.a_tx = txm ? txm_a_tx : kABytes;
+        if (txm) p.kblocks = 3 * P_in * p.nchunk_c;       // stages per tile: one per (tap row, parity row, chunk)
+        p.stages = stages_of(txm, wres, stage); if (p.stages > kMaxStages) p.stages = kMaxStages;
     }
-    p.stages = (200 * 1024) / stage_bytes; if (p.stages > kMaxStages) p.stages = kMaxStages;
+    const int stage_bytes = p.a_slot + (p.wres ? 0 : (p.txm ? 3 : 1) * p.NT * 128);
     p.nprod = p.stages < kProducers ? p.stages : kProducers;
     p.Cout = Cout; p.P_out = P_out;
     p.bias = bias; p.emb = emb; p.emb_stride = emb_stride;
@@ -452,9 +560,11 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     HD_REQUIRE(!chan_sums || (P_out == 1 && out_nchw_c == 0));
     p.chan_sums = chan_sums;
 
-    CUtensorMap mA0, mA1, mB;
+    CUtensorMap mA0, mA1, mB, mOut;
     const int box_w = p.txm ? p.TW + 2 : p.TW;
     int rc = hd_make_act_tmap(&mA0, in0, C0, P_in, N, H, W, 64, box_w, p.TH); if (rc) return rc;
+    if (p.stage_out) { rc = hd_make_act_tmap(&mOut, out, Cout, P_out, N, H, W, 64, p.TW, p.TH); if (rc) return rc; }
+    else mOut = mA0;
     if (C1 > 0) { rc = hd_make_act_tmap(&mA1, in1, C1, 1, N, H, W, 64, box_w, p.TH); if (rc) return rc; }
     else mA1 = mA0;
     {
@@ -463,7 +573,7 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
         uint32_t box[2] = {64, (uint32_t)p.NT};
         rc = hd_make_tmap_bf16(&mB, w, 2, dims, str, box); if (rc) return rc;
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 2 * 256 * 4 + 2 * 512 * 4;
+    const size_t smem = (size_t)p.stages * stage_bytes + (p.stage_out ? 2 * kABytes : 0) + (p.wres ? (size_t)CoutL * p.kb_w * 128 : 0) + 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 2 * 256 * 4 + 2 * 512 * 4;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
@@ -476,11 +586,11 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     }
     int grid = p.m_tiles * p.n_tiles; const int sms = hd_num_sms(); if (grid > sms) grid = sms;
     if (chan_sums) {
-        if (res) conv_tc_kernel<true, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
-        else conv_tc_kernel<true, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
+        if (res) conv_tc_kernel<true, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, p);
+        else conv_tc_kernel<true, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, p);
     } else {
-        if (res) conv_tc_kernel<false, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
-        else conv_tc_kernel<false, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, p);
+        if (res) conv_tc_kernel<false, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, p);
+        else conv_tc_kernel<false, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, p);
     }
     HD_CHECK_LAUNCH();
     return HD_OK;
