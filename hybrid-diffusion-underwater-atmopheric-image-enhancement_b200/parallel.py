@@ -52,10 +52,13 @@ class GradReducer:
         self.buf = None
         self.hi = 0
         self.launched = 0                      # number of collectives issued (tests / bench read it)
+        self.before_reduce = None              # optional callable run before a collective is enqueued (stream joins)
 
     def reduce_async(self, chunk: torch.Tensor):
         if self.world == 1 or chunk.numel() == 0:
             return
+        if self.before_reduce is not None:
+            self.before_reduce()
         chunk.mul_(1.0 / self.world)
         self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.launched += 1
