@@ -40,6 +40,9 @@ PROTOTYPES = {
     "hd_gn_group_sums": [P, I, P, I, I, I, P, P],
     "hd_pad_nchw": [P, I, P, I, L, P],
     "hd_probe_shift": [P, P, P, I, I, P],
+    "hd_conv_dbg_read": [P],
+    "hd_probe_queue": [P, P, I, I, I, I, I, P, P],
+    "hd_probe_pair": [P, P, P, I, I, I, I, P, I, I, I, I, I, P],
     "hd_conv_tc_supported": [I, I, I, I, I, I, I, I],
     "hd_wgrad_tc": [P, I, P, I, I, P, I, I, P, P, L, I, I, I, I, P],
     "hd_wgrad_tc_supported": [I, I, I, I, I, I, I, I],

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhdiff_b200.so")
-SOURCES = ["hd_simt.cu", "hd_fused.cu", "hd_conv_tc.cu", "hd_wgrad_tc.cu", "hd_attn_tc.cu", "hd_attn_wide_tc.cu", "hd_probe.cu"]
+SOURCES = ["hd_simt.cu", "hd_fused.cu", "hd_conv_tc.cu", "hd_wgrad_tc.cu", "hd_attn_tc.cu", "hd_attn_wide_tc.cu", "hd_probe.cu", "hd_probe2.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 

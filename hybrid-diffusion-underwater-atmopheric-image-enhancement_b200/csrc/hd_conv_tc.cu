@@ -25,10 +25,19 @@ constexpr int kProducers = 4;
 // per scheduler the epilogue (address arithmetic, TMEM loads, packing, stores) took ~3300 of the ~3600 cycles per tile of a
 // K = 576 convolution (ncu: epilogue warps 93 % busy, main loop idle) and was the bottleneck.
 constexpr int kEpiWarps = 8;
-constexpr int kFirstExtraProducer = 2 + kEpiWarps;
-constexpr int kThreads = 32 * (2 + kEpiWarps + kProducers - 1);
+// Second MMA issuer (warp 10, another scheduler than warp 1): the two warps take alternate tiles, each with its own TMEM
+// accumulator.  Measured (scripts/probe_queue.py): one thread issues a tcgen05.mma every ~58 cycles at best and everything
+// else it executes (barrier waits, descriptor arithmetic, commits) is added on top — for N <= 128 the tensor pipe never gets
+// ahead of a single issuer, so its gaps are tensor-pipe idle time; a second issuer fills them (24 MMAs in 1154 cycles at
+// N = 64 whatever the gaps, against 693 + gaps per 12 for one).
+constexpr int kSecondMma = 2 + kEpiWarps;
+constexpr int kFirstExtraProducer = kSecondMma + 1;
+constexpr int kThreads = 32 * (3 + kEpiWarps + kProducers - 1);
 constexpr int kABytes = 128 * 128;     // 128 pixels x 64 bf16
 constexpr int kMaxStages = 8;
+
+// HDIFF_CONV_DBG & 4: CTA 0 records (clock64, globaltimer) at its start and end: the SM clock DURING the kernel
+__device__ long long g_conv_dbg[4];
 
 struct ConvTcParams {
     int N, H, W, TH, TW, tiles_x, tiles_y, m_tiles, n_tiles, NT;
@@ -45,6 +54,8 @@ struct ConvTcParams {
                                      // with TMA tensor stores: whole 128-byte lines instead of 32-byte pieces per thread
     int wres, kb_w;                  // wres: the whole packed weight matrix (n_tiles x kb_w blocks of [NT][64] bf16) is loaded ONCE per CTA
                                      // and stays in shared memory; the ring then carries activations only
+    int mma2;                        // two MMA-issuing warps (alternate tiles)
+    int dbg;                         // timing experiments only (HDIFF_CONV_DBG): 1 = epilogue does no work, 2 = producers load nothing
     int nprod;                       // issuing threads in use (<= stages: a producer must never be two ring laps ahead,
                                      // the parity wait on `empty` cannot tell 0 completed phases from 2)
 };
@@ -53,7 +64,8 @@ template <bool kStats, bool kRes>   // kStats: the epilogue also accumulates p.c
                                     // prefetched).  Separate instantiations: the extra registers must not slow the plain epilogue down
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut, const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+               const __grid_constant__ CUtensorMap mapRes, const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = p.NT * 128;
@@ -68,16 +80,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     uint64_t* tempty = bars + 2 * kMaxStages + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
     uint64_t* wfull = bars + 2 * kMaxStages + 5;   // resident weights have landed
-    float* addend = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);     // [2][256]: bias + embedding row of a tile
+    uint64_t* res_full = bars + 2 * kMaxStages + 6; // [2] residual block has landed in staging buffer b (staged epilogue + residual)
+    float* addend = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);     // [2][256]: bias + embedding row of a tile
     float* stat_s = addend + 2 * 256;                                        // [2][256][2]: per-tile channel sums (p.chan_sums)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((p.dbg & 4) && blockIdx.x == 0 && threadIdx.x == 0) {
+        long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_conv_dbg[0] = clock64(); g_conv_dbg[1] = t;
+    }
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB);
-        if (p.stage_out) tma_prefetch_desc(&mapOut);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        if (p.stage_out) { tma_prefetch_desc(&mapOut); if (kRes) tma_prefetch_desc(&mapRes); }
+        // two issuers: a stage is released by BOTH (its owner's tcgen05.commit + a plain arrive of the other, who only watched
+        // it fill), so neither can fall a ring lap behind — a parity wait cannot tell phase L from phase L + 2
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.mma2 ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
         mbar_init(wfull, 1);
+        mbar_init(&res_full[0], 1); mbar_init(&res_full[1], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -116,6 +136,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             for (int cc = 0; cc < p.nchunk_c; ++cc) {
                                 if (turn == prod) {
                                     mbar_wait(&empty[stage], phase ^ 1);
+                                    if (p.dbg & 2) { mbar_arrive(&full[stage]); goto txm_next; }
+                                    {
                                     mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_tx);
                                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                                     if (cc < p.nchunk0) tma_load_5d(sa, &mapA0, &full[stage], cc * 64, x0 - 1, py, y0 + ty - 1, n);
@@ -124,7 +146,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                     if (!p.wres)
                                         for (int tx = 0; tx < 3; ++tx)
                                             tma_load_2d(sa + p.a_slot + tx * b_bytes, &mapB, &full[stage], (kb0 + tx * tap_stride) * 64, n_tile * p.NT);
+                                    }
                                 }
+                                txm_next:
                                 if (++turn == p.nprod) turn = 0;
                                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
                             }
@@ -148,44 +172,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             }
             }
         }
-    } else if (warp == 1) {
-        if (elect_one()) {
+    } else if (warp == 1 || warp == kSecondMma) {
+        const int me = warp == 1 ? 0 : 1;            // this issuer's tile parity = its accumulator
+        if ((me == 0 || p.mma2) && elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
             int stage = 0; uint32_t phase = 0; int it = 0;
             if (p.wres) { mbar_wait(wfull, 0); tc_fence_after(); }
             const int per_row = p.P_in * p.nchunk_c;     // txm: stages per tap row = K blocks between two tap columns
+            // descriptor low words (see umma_desc_lo): everything below is 32-bit adds on them
+            const uint32_t ring_lo = umma_desc_lo(smem_u32(smem));
+            const uint32_t st16 = (uint32_t)stage_bytes >> 4, aslot16 = (uint32_t)p.a_slot >> 4, b16 = (uint32_t)b_bytes >> 4;
+            const uint32_t wres_lo = umma_desc_lo(smem_u32(wres_buf));
+            const uint32_t bstep = p.wres ? (uint32_t)per_row * b16 : b16;         // between the B tiles of two tap columns (txm)
+            uint32_t a_lo = ring_lo;                     // A operand of the current stage
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
+                if (p.mma2 && acc != me) {               // the other issuer's tile: watch its stages fill, in order
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        mbar_arrive(&empty[stage]);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                    a_lo = ring_lo + (uint32_t)stage * st16;
+                    continue;
+                }
                 mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
-                const uint32_t wb = smem_u32(wres_buf) + (uint32_t)((tile % p.n_tiles) * p.kb_w * b_bytes);
-                int kb0 = 0, in_row = 0;                 // txm + resident weights: first K block (tap column 0) of this stage
+                const uint32_t wb_lo = wres_lo + (uint32_t)((tile % p.n_tiles) * p.kb_w) * b16;
+                uint32_t wk_lo = wb_lo;                  // resident weights: B tile of this stage's first K block
+                int in_row = 0;
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t b_lo = p.wres ? wk_lo : a_lo + aslot16;
                     if (p.txm) {
 #pragma unroll
-                        for (int tx = 0; tx < 3; ++tx) {
-                            const uint64_t adesc = umma_smem_desc(sa + tx * 128, 16, 1024);      // halo box, shifted by tx pixels
-                            const uint64_t bdesc = umma_smem_desc(p.wres ? wb + (uint32_t)((kb0 + tx * per_row) * b_bytes)
-                                                                         : sa + p.a_slot + tx * b_bytes, 16, 1024);
+                        for (int tx = 0; tx < 3; ++tx)                    // halo box shifted by tx pixels = tx rows of 128 B
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | tx | k) != 0);
-                        }
-                        ++kb0;
-                        if (++in_row == per_row) { in_row = 0; kb0 += 2 * per_row; }
+                                umma_bf16_lo(d_tmem, a_lo + tx * 8 + 2 * k, b_lo + tx * bstep + 2 * k, idesc, (kb | tx | k) != 0);
+                        wk_lo += b16;
+                        if (++in_row == per_row) { in_row = 0; wk_lo += 2 * (uint32_t)per_row * b16; }
                     } else {
-                    const uint64_t adesc = umma_smem_desc(sa, 16, 1024);
-                    const uint64_t bdesc = umma_smem_desc(p.wres ? wb + (uint32_t)(kb * b_bytes) : sa + p.a_slot, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)      // 4 x (K = 16): advance 32 bytes inside the 128-byte swizzle atom
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < 4; ++k)      // 4 x (K = 16): advance 32 bytes inside the 128-byte swizzle atom
+                            umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0);
+                        wk_lo += b16;
                     }
                     umma_commit(&empty[stage]);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    a_lo += st16;
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = ring_lo; }
                 }
                 umma_commit(&tfull[acc]);
             }
@@ -198,6 +235,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int ty = row / p.TW, tx = row % p.TW;
         int it = 0;
         uint32_t sb = 0;                             // staged 64-channel blocks so far (p.stage_out): buffer = sb & 1
+        // staged epilogue + residual: the residual block is brought into the staging buffer by TMA one block ahead (issued
+        // by thread 0 right after the barrier that frees the buffer) and the output is formed in place over it
+        auto res_load = [&](int tl, int blk, uint32_t buf) {
+            const int nt = tl % p.n_tiles, mt = tl / p.n_tiles;
+            const int txi = mt % p.tiles_x; const int rr = mt / p.tiles_x;
+            const int tyi = rr % p.tiles_y; const int nn = rr / p.tiles_y;
+            const int j0 = nt * p.NT + blk * 64;
+            const int cv_w = p.P_out * p.Cout;
+            const int py = j0 / cv_w;
+            mbar_arrive_expect_tx(&res_full[buf], kABytes);
+            tma_load_5d(stage_buf + buf * kABytes, &mapRes, &res_full[buf], j0 - py * cv_w, txi * p.TW, py, tyi * p.TH, nn);
+        };
+        if (kRes && p.stage_out && etid == 0 && (int)blockIdx.x < total_tiles) res_load(blockIdx.x, 0, 0);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
@@ -233,7 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const long long pix2 = (((long long)n * (2 * p.H) + 2 * y) * (2 * p.W) + 2 * x) * p.Cout;
             const long long q_dx = p.Cout, q_dy = 2ll * p.W * p.Cout;
             uint4 pre_a[2], pre_b[2];
-            const bool have_pre = kRes && valid && !p.out_nchw && half * 16 < p.NT;
+            const bool have_pre = kRes && valid && !p.out_nchw && !p.stage_out && half * 16 < p.NT;
             if (have_pre) {
                 const int c0 = half * 16;
                 long long o;
@@ -254,6 +304,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
+            if (p.dbg & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (has_next && etid < p.NT) addend[(acc ^ 1) * 256 + etid] = a_next;
+                continue;
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
             if (p.out_nchw) {
                 if (n_tile == 0 && half == 0) {
@@ -284,17 +341,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         f[4 * i] = __uint_as_float(v[4 * i]) + a.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + a.y;
                         f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + a.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + a.w;
                     }
-                    if (kRes) {
-                        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
-                        if (pre) { r0 = pre[0]; r1 = pre[1]; }
-                        else if (valid) {
-                            const int j = n_tile * p.NT + c;
-                            long long off;
-                            if (p.P_out == 1) off = pix1 + j;
-                            else { const int q = j / p.Cout, cph = j - q * p.Cout; off = pix2 + (q >> 1) * q_dy + (q & 1) * q_dx + cph; }
-                            const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
-                            r0 = __ldg(rp); r1 = __ldg(rp + 1);
-                        }
+                    if (kRes) {          // the residual block sits (swizzled) where the output is about to be written
+                        const uint4 r0 = *reinterpret_cast<const uint4*>(srow + ((cb ^ (row & 7)) << 4));
+                        const uint4 r1 = *reinterpret_cast<const uint4*>(srow + (((cb + 1) ^ (row & 7)) << 4));
                         const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
                         const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
 #pragma unroll
@@ -316,8 +365,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     tmem_ld16(taddr + c + 32, vb);
                     tmem_wait_ld();
                     uint8_t* sbuf = stage_buf + (sb & 1) * kABytes;
-                    stage_emit(va, c, sbuf + row * 128, half * 2, first && have_pre ? pre_a : nullptr);
-                    stage_emit(vb, c + 32, sbuf + row * 128, half * 2 + 4, first && have_pre ? pre_b : nullptr);
+                    if (kRes) mbar_wait(&res_full[sb & 1], (sb >> 1) & 1);
+                    stage_emit(va, c, sbuf + row * 128, half * 2, nullptr);
+                    stage_emit(vb, c + 32, sbuf + row * 128, half * 2 + 4, nullptr);
                     fence_proxy_async_smem();
                     if (etid == 0) bulk_wait_group_read0();
                     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -329,6 +379,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const int py = j0 / cv_w;
                         tma_store_5d(&mapOut, sbuf, j0 - py * cv_w, tx_i * p.TW, py, ty_i * p.TH, n);
                         bulk_commit_group();
+                        if (kRes) {      // the other buffer is free (its store was read out before the barrier): fetch the next block
+                            if (c + 64 < p.NT) res_load(tile, (c - half * 16) / 64 + 1, (sb + 1) & 1);
+                            else if (has_next) res_load(tile + gridDim.x, 0, (sb + 1) & 1);
+                        }
                     }
                     ++sb;
                 }
@@ -427,6 +481,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if ((p.dbg & 4) && blockIdx.x == 0 && threadIdx.x == 0) {
+        long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_conv_dbg[2] = clock64(); g_conv_dbg[3] = t;
+    }
 }
 
 int pick_nt(int CoutL) {
@@ -547,6 +605,12 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
                     if (stages_of(t, w, g) >= (t ? 3 : 2)) { txm = t; wres = w; stage = g; found = true; }
         HD_REQUIRE(found);
         p.txm = txm; p.wres = wres; p.stage_out = stage;
+        static const int dbg = getenv("HDIFF_CONV_DBG") ? atoi(getenv("HDIFF_CONV_DBG")) : 0;
+        p.dbg = dbg;
+        // second issuer: a gain where the issuing thread is the bottleneck (N <= 64: 64->64 0.201 -> 0.178 ms), a small loss
+        // where the ring fill is (N = 128: +5 %, the watcher's arrive delays the release of a stage).  HDIFF_CONV_MMA2=0/1 forces it.
+        static const int mma2_env = getenv("HDIFF_CONV_MMA2") ? atoi(getenv("HDIFF_CONV_MMA2")) : -1;
+        p.mma2 = mma2_env >= 0 ? (mma2_env ? 1 : 0) : (p.NT <= 64 ? 1 : 0);
         p.a_slot = txm ? txm_a_slot : kABytes; p.a_tx = txm ? txm_a_tx : kABytes;
         if (txm) p.kblocks = 3 * P_in * p.nchunk_c;       // stages per tile: one per (tap row, parity row, chunk)
         p.stages = stages_of(txm, wres, stage); if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -560,11 +624,13 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     HD_REQUIRE(!chan_sums || (P_out == 1 && out_nchw_c == 0));
     p.chan_sums = chan_sums;
 
-    CUtensorMap mA0, mA1, mB, mOut;
+    CUtensorMap mA0, mA1, mB, mOut, mRes;
     const int box_w = p.txm ? p.TW + 2 : p.TW;
     int rc = hd_make_act_tmap(&mA0, in0, C0, P_in, N, H, W, 64, box_w, p.TH); if (rc) return rc;
     if (p.stage_out) { rc = hd_make_act_tmap(&mOut, out, Cout, P_out, N, H, W, 64, p.TW, p.TH); if (rc) return rc; }
     else mOut = mA0;
+    if (p.stage_out && res) { rc = hd_make_act_tmap(&mRes, res, Cout, P_out, N, H, W, 64, p.TW, p.TH); if (rc) return rc; }
+    else mRes = mA0;
     if (C1 > 0) { rc = hd_make_act_tmap(&mA1, in1, C1, 1, N, H, W, 64, box_w, p.TH); if (rc) return rc; }
     else mA1 = mA0;
     {
@@ -573,7 +639,7 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
         uint32_t box[2] = {64, (uint32_t)p.NT};
         rc = hd_make_tmap_bf16(&mB, w, 2, dims, str, box); if (rc) return rc;
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + (p.stage_out ? 2 * kABytes : 0) + (p.wres ? (size_t)CoutL * p.kb_w * 128 : 0) + 1024 /*align slack*/ + (2 * kMaxStages + 6) * 8 + 2 * 256 * 4 + 2 * 512 * 4;
+    const size_t smem = (size_t)p.stages * stage_bytes + (p.stage_out ? 2 * kABytes : 0) + (p.wres ? (size_t)CoutL * p.kb_w * 128 : 0) + 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 2 * 256 * 4 + 2 * 512 * 4;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
@@ -586,12 +652,19 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     }
     int grid = p.m_tiles * p.n_tiles; const int sms = hd_num_sms(); if (grid > sms) grid = sms;
     if (chan_sums) {
-        if (res) conv_tc_kernel<true, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, p);
-        else conv_tc_kernel<true, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, p);
+        if (res) conv_tc_kernel<true, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
+        else conv_tc_kernel<true, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
     } else {
-        if (res) conv_tc_kernel<false, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, p);
-        else conv_tc_kernel<false, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, p);
+        if (res) conv_tc_kernel<false, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
+        else conv_tc_kernel<false, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
     }
     HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+
+// timing experiments: (clock64, globaltimer ns) at the start and the end of CTA 0 of the last hd_conv_tc launch with HDIFF_CONV_DBG & 4
+extern "C" int hd_conv_dbg_read(long long* out4) {
+    HD_REQUIRE(out4);
+    if (cudaMemcpyFromSymbol(out4, g_conv_dbg, sizeof(long long) * 4) != cudaSuccess) { hd_set_error("cudaMemcpyFromSymbol"); return HD_ERR_CUDA; }
     return HD_OK;
 }

@@ -144,6 +144,23 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= 2ull << 61;                 // SWIZZLE_128B
     return d;
 }
+// The descriptor of a dense 128B-swizzled K-major operand (LBO 16, SBO 1024) is a constant high word and a low word that
+// is LINEAR in the shared-memory address, so the issuing thread can step through stages / taps / K slices with one 32-bit
+// add per operand instead of rebuilding the descriptor (shifts, masks, ors) in front of every MMA.  Measured on B200
+// (scripts/probe_pair.py + HDIFF_CONV_DBG): the tensor pipe needs 57 / 67 cycles per 128xNx16 MMA at N = 64 / 128, but its
+// queue is short — ~85 instructions of descriptor arithmetic between a stage's barrier wait and its first MMA left it idle
+// for ~350 cycles per stage.
+constexpr uint32_t kUmmaDescHi128 = 0x40004040u;             // SBO 1024 >> 4 | version 1 << 14 | SWIZZLE_128B (2) << 29
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | 0x10000u; }
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHi128) : "memory");
+}
 // instruction descriptor for kind::f16, bf16 inputs, fp32 accumulate
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |

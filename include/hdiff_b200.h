@@ -133,8 +133,18 @@ int hd_sampler_step(float* x, const float* eps_c, const float* eps_u, const floa
                     const int* step_ptr, int last_step_clip, int* nan_flag, int64_t n, hd_stream_t stream);
 int hd_add_int(int* p, int delta, hd_stream_t stream);
 
+/* timing experiments (HDIFF_CONV_DBG=4): (clock64, globaltimer ns) at the start / end of CTA 0 of the last hd_conv_tc launch */
+int hd_conv_dbg_read(long long* out4);
 /* ---- hardware probe (scripts/probe_shift.py): tcgen05 A operand starting at an arbitrary 128-byte row of a swizzled box ---- */
 int hd_probe_shift(const void* x, const void* w, float* out, int shift, int mode, hd_stream_t stream);
+/* ---- hardware probe (scripts/probe_pair.py): C[256][N] = A[256][K] B[N][K]^T by a CTA pair; mode 1 = each CTA on its own
+ *      (tcgen05.mma.cta_group::1), mode 2 = one M = 256 MMA stream for the pair (cta_group::2, each CTA holds half of B);
+ *      out accumulates `reps` identical products, cycles[2] = clock64 span of the MMA sequence per CTA ---- */
+int hd_probe_pair(const void* a, const void* b, float* out, int N, int K, int mode, int reps, long long* cycles, int shift,
+                  int fill, int cper, int nclusters, int ring, hd_stream_t stream);
+/* how far the issuing thread can run ahead of the tensor pipe: `groups` x (12 unrolled MMAs + `gap` idle cycles) */
+int hd_probe_queue(const void* a, const void* b, int N, int groups, int gap, int issuers, int second_warp, long long* cycles,
+                   hd_stream_t stream);
 
 /* ---- clip_grad_norm_ + AdamW on the flat buffers (TrainCondition.py:39,61-63) ---- */
 int hd_sqnorm(const float* g, int64_t n, double* out, hd_stream_t stream);
