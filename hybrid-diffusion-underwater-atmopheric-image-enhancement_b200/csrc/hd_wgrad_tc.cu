@@ -18,7 +18,11 @@ namespace {
 // warp 0 + warps 6..: TMA producers (a stage is up to 12 tensor copies; one issuing thread is the bottleneck, so the
 // copies of a stage are dealt round-robin to kProducers threads), warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int kProducers = 4;
-constexpr int kThreads = 192 + 32 * (kProducers - 1);
+// warp 6: second MMA issuer (another scheduler than warp 1).  One thread issues a tcgen05.mma every ~58 cycles at best and
+// everything else it executes is added on top (scripts/probe_queue.py), so for N <= 128 its gaps are tensor-pipe idle time;
+// the two issuers take the even / odd accumulator groups of every stage and release it together.
+constexpr int kSecondMma = 6;
+constexpr int kThreads = 224 + 32 * (kProducers - 1);
 constexpr int kBlkBytes = 64 * 128;    // one [64 pixels][64 channels] bf16 box
 constexpr int kMaxStages = 8;
 
@@ -83,8 +87,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapX0); tma_prefetch_desc(&mapX1); tma_prefetch_desc(&mapDY);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], kProducers); mbar_init(&empty[s], 1); }
-        mbar_init(tfull, 1);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], kProducers); mbar_init(&empty[s], 2); }
+        mbar_init(tfull, 2);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -93,8 +97,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 || warp >= 6) {
-        const int prod = warp == 0 ? 0 : warp - 5;
+    if (warp == 0 || warp > kSecondMma) {
+        const int prod = warp == 0 ? 0 : warp - kSecondMma;
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             // bytes this producer brings per stage: copies b (0 .. 2G+nb-1) with b % kProducers == prod
@@ -166,7 +170,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
                 if (++tx_i == p.tiles_x) { tx_i = 0; if (++ty_i == p.tiles_y) { ty_i = 0; ++n; } }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == kSecondMma) {
+        const int me = warp == 1 ? 0 : 1;            // this issuer takes the accumulator groups g with g % 2 == me
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, p.NT, 1, 1);
             int stage = 0; uint32_t phase = 0;
@@ -185,23 +190,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
             } else {
                 for (int g = 0; g < 8; ++g) { a_off[g] = g * 2 * kBlkBytes; a_lbo[g] = kBlkBytes; }
             }
+            // descriptor LOW words for ring stage 0 (address >> 4 | LBO >> 4 << 16; the high word — SBO 1024, version, 128-byte
+            // swizzle — is one constant): stepping through stages and K slices is then a 32-bit add per operand
+            const uint32_t ring = smem_u32(smem);
+            uint32_t a_lo[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) a_lo[g] = (((ring + a_off[g]) & 0x3FFFF) >> 4) | (((a_lbo[g] >> 4) & 0x3FFF) << 16);
+            const uint32_t b_lo0 = (((ring + (uint32_t)a_bytes) & 0x3FFFF) >> 4) | (((uint32_t)kBlkBytes >> 4) << 16);
+            const uint32_t st16 = (uint32_t)stage_bytes >> 4;
+            uint32_t soff = 0;                       // (stage * stage_bytes) >> 4
             for (int s = 0; s < nsteps; ++s) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t sb = sa + a_bytes;
+                const uint32_t b_lo = b_lo0 + soff;
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     if (g >= p.G) break;
+                    if ((g & 1) != me) continue;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {    // K = 16 pixels = 2 groups of 8 rows = 2048 bytes
-                        const uint64_t adesc = umma_smem_desc(sa + a_off[g] + k * 2048, a_lbo[g], 1024);
-                        const uint64_t bdesc = umma_smem_desc(sb + k * 2048, kBlkBytes, 1024);
-                        umma_bf16(tmem_base + g * p.NT, adesc, bdesc, idesc, (s | k) != 0);
-                    }
+                    for (int k = 0; k < 4; ++k)      // K = 16 pixels = 2 groups of 8 rows = 2048 bytes
+                        umma_bf16_lo(tmem_base + g * p.NT, a_lo[g] + soff + k * 128, b_lo + k * 128, idesc, (s | k) != 0);
                 }
-                umma_commit(&empty[stage]);
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                umma_commit(&empty[stage]);          // (an issuer without groups arrives at once)
+                soff += st16;
+                if (++stage == p.stages) { stage = 0; phase ^= 1; soff = 0; }
             }
             umma_commit(tfull);
         }
