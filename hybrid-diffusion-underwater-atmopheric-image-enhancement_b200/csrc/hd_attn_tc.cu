@@ -212,6 +212,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnFwdPara
 // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: softmax of group 0, warps 6-9: softmax of group 1.
 // TMEM (512 columns): group g at g*256: S/P 64 | Q 64 | O 128.
 // ---------------------------------------------------------------------------------------------
+// (A second MMA issuer, one per query group, was tried and made this kernel SLOWER: 1.07 -> 1.52 ms at N = 8, S = 16384.  The single
+// issuer is what staggers the two groups — S of one group is issued right behind P V of the other — and two free-running issuers
+// let both groups reach their softmax phase together, leaving the tensor pipe idle.)
 constexpr int kF2Threads = 64 + 256;
 constexpr int kF2Stages = 6;
 constexpr uint32_t kF2S = 0, kF2Q = 64, kF2O = 128, kF2Group = 256;
@@ -444,7 +447,13 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 
 // 8 element-wise warps: two per TMEM lane quarter, each owning 32 of the 64 score columns of a tile (a single warp per
 // scheduler cannot hide the MUFU / TMEM-load latencies of 128 values per thread and would leave the tensor pipe idle)
-constexpr int kBwdThreads = 64 + 256;
+// warp 10: second MMA issuer.  One thread issues a tcgen05.mma every ~58 cycles at best (scripts/probe_queue.py) and a tile
+// needs 24 (20 in the dQ pass): 1 390 cycles of issue against 1 024 of tensor-pipe time.  The work is split by TMEM buffer
+// family so that every write-after-read ordering stays inside one in-order issuer:
+//   issuer 0: St = X0 Y0^T  and  acc1 += P Y1    (P lives in the St columns)
+//   issuer 1: dPt = X1 Y1^T and  acc0 += dS Y0   (dS lives in the dPt columns)
+constexpr int kBwdSecondMma = 10;
+constexpr int kBwdThreads = 64 + 256 + 32;
 
 template <bool kDQ>
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -480,9 +489,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapQKV); tma_prefetch_desc(&mapDO);
         mbar_init(x_full, kXT ? 8 : 1);               // kXT: one arrival per element-wise warp (operands stored to TMEM)
-        for (int s = 0; s < kNS; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); }
-        mbar_init(acc_done, 1);
+        for (int s = 0; s < kNS; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 2); }       // both issuers release a tile
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 2); mbar_init(&p_full[b], 8); }
+        mbar_init(acc_done, 2);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -514,30 +523,32 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
                 if (++stage == kNS) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == kBwdSecondMma) {
+        const int me = warp == 1 ? 0 : 1;
         if (elect_one()) {
             const uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);
             const uint32_t idesc_acc = umma_idesc_bf16(BM, D, 0, 1);
-            const uint32_t aX0 = smem_u32(sX0), aX1 = smem_u32(sX1);
+            // issuer 0: scores from (X0, Y0), accumulates acc1 from P (St columns) and Y1
+            // issuer 1: scores from (X1, Y1), accumulates acc0 from dS (dPt columns) and Y0
+            const uint32_t aX = smem_u32(me == 0 ? sX0 : sX1);
+            const uint32_t colS = me == 0 ? kColSt : kColdPt;                  // this issuer's score buffers
+            const uint32_t colX = me == 0 ? kColX0 : kColX1;                   // its stationary operand in TMEM (dQ pass)
+            const uint32_t colAcc = me == 0 ? kColAcc1 : kColAcc0;
+            const uint32_t yS = me == 0 ? 0 : kYBytes;                         // score operand inside a ring stage
+            const uint32_t yA = me == 0 ? kYBytes : 0;                         // accumulation operand (the OTHER Y tile, MN-major)
+            const bool has_acc = !(kDQ && me == 0);                            // the dQ pass has no acc1
             int ld_stage = 0; uint32_t ld_phase = 0;
             auto issue_s = [&](int j) {
                 mbar_wait(&y_full[ld_stage], ld_phase);
                 tc_fence_after();
-                const uint32_t aY0 = smem_u32(sY + ld_stage * 2 * kYBytes), aY1 = aY0 + kYBytes;
+                const uint32_t aY = smem_u32(sY + ld_stage * 2 * kYBytes) + yS;
                 const uint32_t b = (uint32_t)(j & 1) * 64;
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     const int blk = kk >> 2, sub = kk & 3;
-                    const uint64_t bd = umma_smem_desc(aY0 + blk * 8192 + sub * 32, 16, 1024);
-                    if (kXT) umma_bf16_ts(tmem_base + kColSt + b, tmem_base + kColX0 + kk * 8, bd, idesc_s, kk != 0);
-                    else umma_bf16(tmem_base + kColSt + b, umma_smem_desc(aX0 + blk * (kXBytes / 2) + sub * 32, 16, 1024), bd, idesc_s, kk != 0);
-                }
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const int blk = kk >> 2, sub = kk & 3;
-                    const uint64_t bd = umma_smem_desc(aY1 + blk * 8192 + sub * 32, 16, 1024);
-                    if (kXT) umma_bf16_ts(tmem_base + kColdPt + b, tmem_base + kColX1 + kk * 8, bd, idesc_s, kk != 0);
-                    else umma_bf16(tmem_base + kColdPt + b, umma_smem_desc(aX1 + blk * (kXBytes / 2) + sub * 32, 16, 1024), bd, idesc_s, kk != 0);
+                    const uint64_t bd = umma_smem_desc(aY + blk * 8192 + sub * 32, 16, 1024);
+                    if (kXT) umma_bf16_ts(tmem_base + colS + b, tmem_base + colX + kk * 8, bd, idesc_s, kk != 0);
+                    else umma_bf16(tmem_base + colS + b, umma_smem_desc(aX + blk * (kXBytes / 2) + sub * 32, 16, 1024), bd, idesc_s, kk != 0);
                 }
                 umma_commit(&s_full[j & 1]);
                 if (++ld_stage == kNS) { ld_stage = 0; ld_phase ^= 1; }
@@ -547,26 +558,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
             issue_s(0);
             int stage = 0;
             for (int j = 0; j < T; ++j) {
-                // scores of tile j+1 go to the other buffer.  Its last readers were the accumulation MMAs of tile j-1, issued
-                // earlier by this thread (the tensor pipe executes in issue order), and the element-wise loads of tile j-1,
-                // which completed before p_full of tile j-1 — already waited for.
+                // scores of tile j+1 go to the other buffer.  Its last readers were this issuer's accumulation MMAs of tile j-1
+                // (the tensor pipe executes one thread's MMAs in issue order) and the element-wise loads of tile j-1, which
+                // completed before p_full of tile j-1 — already waited for.
                 if (j + 1 < T) issue_s(j + 1);
                 mbar_wait(&p_full[j & 1], (j >> 1) & 1);
                 tc_fence_after();
-                const uint32_t aY0 = smem_u32(sY + stage * 2 * kYBytes), aY1 = aY0 + kYBytes;
-                const uint32_t b = (uint32_t)(j & 1) * 64;
-                // P / dS sit in the first 16 columns of each warp's 32-column range: K steps 0,1 -> +0,+8 ; 2,3 -> +32,+40
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16_ts(tmem_base + kColAcc0, tmem_base + kColdPt + b + (kk >> 1) * 32 + (kk & 1) * 8,
-                                 umma_smem_desc(aY0 + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0);
-                if (!kDQ) {
+                if (has_acc) {
+                    const uint32_t aY = smem_u32(sY + stage * 2 * kYBytes) + yA;
+                    const uint32_t b = (uint32_t)(j & 1) * 64;
+                    // P / dS sit in the first 16 columns of each warp's 32-column range: K steps 0,1 -> +0,+8 ; 2,3 -> +32,+40
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16_ts(tmem_base + kColAcc1, tmem_base + kColSt + b + (kk >> 1) * 32 + (kk & 1) * 8,
-                                     umma_smem_desc(aY1 + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0);
+                        umma_bf16_ts(tmem_base + colAcc, tmem_base + colS + b + (kk >> 1) * 32 + (kk & 1) * 8,
+                                     umma_smem_desc(aY + kk * 2048, 8192, 1024), idesc_acc, (j | kk) != 0);
                 }
-                umma_commit(&y_empty[stage]);
+                umma_commit(&y_empty[stage]);        // covers this issuer's score MMAs on the tile as well
                 if (++stage == kNS) stage = 0;
             }
             umma_commit(acc_done);
