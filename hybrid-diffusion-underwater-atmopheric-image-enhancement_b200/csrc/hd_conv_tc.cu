@@ -54,7 +54,9 @@ struct ConvTcParams {
                                      // with TMA tensor stores: whole 128-byte lines instead of 32-byte pieces per thread
     int wres, kb_w;                  // wres: the whole packed weight matrix (n_tiles x kb_w blocks of [NT][64] bf16) is loaded ONCE per CTA
                                      // and stays in shared memory; the ring then carries activations only
-    int mma2;                        // two MMA-issuing warps (alternate tiles)
+    int mma2;                        // two MMA-issuing warps: 1 = alternate tiles (one accumulator each), 2 = both work on every stage,
+                                     // each on half of its K slices into its own PARTIAL accumulator (column offset 128; NT <= 128);
+                                     // the epilogue adds the two partials
     int dbg;                         // timing experiments only (HDIFF_CONV_DBG): 1 = epilogue does no work, 2 = producers load nothing
     int nprod;                       // issuing threads in use (<= stages: a producer must never be two ring laps ahead,
                                      // the parity wait on `empty` cannot tell 0 completed phases from 2)
@@ -95,7 +97,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // two issuers: a stage is released by BOTH (its owner's tcgen05.commit + a plain arrive of the other, who only watched
         // it fill), so neither can fall a ring lap behind — a parity wait cannot tell phase L from phase L + 2
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.mma2 ? 2 : 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], p.mma2 == 2 ? 2 : 1); mbar_init(&tempty[a], kEpiWarps); }
         mbar_init(wfull, 1);
         mbar_init(&res_full[0], 1); mbar_init(&res_full[1], 1);
         fence_barrier_init();
@@ -187,6 +189,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             uint32_t a_lo = ring_lo;                     // A operand of the current stage
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
+                if (p.mma2 == 2) {
+                    // both issuers, every stage: K slices k = me, me + 2 of each operand pair into partial accumulator `me`
+                    mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_part = tmem_base + acc * 256 + me * 128;
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t b_lo = a_lo + aslot16;
+                        if (p.txm) {
+#pragma unroll
+                            for (int tx = 0; tx < 3; ++tx)
+#pragma unroll
+                                for (int i = 0; i < 2; ++i)
+                                    umma_bf16_lo(d_part, a_lo + tx * 8 + 4 * i + 2 * me, b_lo + tx * b16 + 4 * i + 2 * me, idesc, (kb | tx | i) != 0);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                umma_bf16_lo(d_part, a_lo + 4 * i + 2 * me, b_lo + 4 * i + 2 * me, idesc, (kb | i) != 0);
+                        }
+                        umma_commit(&empty[stage]);
+                        a_lo += st16;
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = ring_lo; }
+                    }
+                    umma_commit(&tfull[acc]);
+                    continue;
+                }
                 if (p.mma2 && acc != me) {               // the other issuer's tile: watch its stages fill, in order
                     for (int kb = 0; kb < p.kblocks; ++kb) {
                         mbar_wait(&full[stage], phase);
@@ -317,6 +346,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     uint32_t v[16];
                     tmem_ld16(taddr, v);
                     tmem_wait_ld();
+                    if (p.mma2 == 2) {
+                        uint32_t v2[16];
+                        tmem_ld16(taddr + 128, v2);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+                    }
                     if (valid) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -364,6 +400,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     tmem_ld16(taddr + c, va);
                     tmem_ld16(taddr + c + 32, vb);
                     tmem_wait_ld();
+                    if (p.mma2 == 2) {                  // add the second issuer's partial accumulator
+                        uint32_t wa[16], wb[16];
+                        tmem_ld16(taddr + 128 + c, wa);
+                        tmem_ld16(taddr + 128 + c + 32, wb);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            va[i] = __float_as_uint(__uint_as_float(va[i]) + __uint_as_float(wa[i]));
+                            vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __uint_as_float(wb[i]));
+                        }
+                    }
                     uint8_t* sbuf = stage_buf + (sb & 1) * kABytes;
                     if (kRes) mbar_wait(&res_full[sb & 1], (sb >> 1) & 1);
                     stage_emit(va, c, sbuf + row * 128, half * 2, nullptr);
@@ -455,6 +502,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     tmem_ld16(taddr + c, va);
                     if (two) tmem_ld16(taddr + c + 32, vb);
                     tmem_wait_ld();
+                    if (p.mma2 == 2) {                  // add the second issuer's partial accumulator
+                        uint32_t wa[16], wb[16];
+                        tmem_ld16(taddr + 128 + c, wa);
+                        if (two) tmem_ld16(taddr + 128 + c + 32, wb);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            va[i] = __float_as_uint(__uint_as_float(va[i]) + __uint_as_float(wa[i]));
+                            if (two) vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __uint_as_float(wb[i]));
+                        }
+                    }
                     float fa[16], fb[16];
                     if (valid) {
                         emit(va, c, fa, first && have_pre ? pre_a : nullptr);
@@ -607,10 +665,17 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
         p.txm = txm; p.wres = wres; p.stage_out = stage;
         static const int dbg = getenv("HDIFF_CONV_DBG") ? atoi(getenv("HDIFF_CONV_DBG")) : 0;
         p.dbg = dbg;
-        // second issuer: a gain where the issuing thread is the bottleneck (N <= 64: 64->64 0.201 -> 0.178 ms), a small loss
-        // where the ring fill is (N = 128: +5 %, the watcher's arrive delays the release of a stage).  HDIFF_CONV_MMA2=0/1 forces it.
+        // second issuer.  Mode 1 (alternate tiles): a gain where the issuing thread is the bottleneck (64->64: 0.201 -> 0.178 ms),
+        // a small loss at N = 128 (+5 %: the watcher's arrive delays the release of a stage).  Mode 2 (both issuers on every
+        // stage, partial accumulators): the same at 64->64, no loss at N = 128 (ring-fill bound: 0.139 ms either way) and a
+        // further gain on tiles with many stages (128+64 -> 64: 0.473 -> 0.438 ms); inside a training step it is slower than mode 1
+        // on the 3-stage 64->64 tiles and on 1x1 layers.  HDIFF_CONV_MMA2=0/1/2 forces a mode.
         static const int mma2_env = getenv("HDIFF_CONV_MMA2") ? atoi(getenv("HDIFF_CONV_MMA2")) : -1;
-        p.mma2 = mma2_env >= 0 ? (mma2_env ? 1 : 0) : (p.NT <= 64 ? 1 : 0);
+        int mode = 0;                                   // by shape, from per-layer timings inside a training step
+        if (p.NT <= 64) mode = (ksize == 1 || p.kblocks <= 3) ? 1 : 2;
+        else if (p.NT <= 128 && ksize == 3) mode = (p.txm && P_in == 1) ? 0 : 2;
+        p.mma2 = mma2_env >= 0 ? mma2_env : mode;
+        if (p.mma2 == 2 && (p.NT > 128 || p.wres || chan_sums)) p.mma2 = p.NT <= 64 ? 1 : 0;
         p.a_slot = txm ? txm_a_slot : kABytes; p.a_tx = txm ? txm_a_tx : kABytes;
         if (txm) p.kblocks = 3 * P_in * p.nchunk_c;       // stages per tile: one per (tap row, parity row, chunk)
         p.stages = stages_of(txm, wres, stage); if (p.stages > kMaxStages) p.stages = kMaxStages;
