@@ -452,6 +452,9 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 // family so that every write-after-read ordering stays inside one in-order issuer:
 //   issuer 0: St = X0 Y0^T  and  acc1 += P Y1    (P lives in the St columns)
 //   issuer 1: dPt = X1 Y1^T and  acc0 += dS Y0   (dS lives in the dPt columns)
+// (16 element-wise warps with 16 columns each instead of 8 x 32 were tried: identical time, 2.82 ms at N = 8, S = 16384 — the
+// element-wise chain is not the limit.  The pass is bound by its MMA mix: 16 SS MMAs of N = 64 per tile cost 48-57 cycles
+// each (probe: 57 for one issuer, 48 for two, against 32 of math) + 8 of N = 128 at 64 = 1 300-1 400 of the ~1 570 cycles.)
 constexpr int kBwdSecondMma = 10;
 constexpr int kBwdThreads = 64 + 256 + 32;
 
