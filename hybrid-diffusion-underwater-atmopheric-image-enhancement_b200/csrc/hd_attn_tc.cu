@@ -214,7 +214,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const AttnFwdPara
 // ---------------------------------------------------------------------------------------------
 // (A second MMA issuer, one per query group, was tried and made this kernel SLOWER: 1.07 -> 1.52 ms at N = 8, S = 16384.  The single
 // issuer is what staggers the two groups — S of one group is issued right behind P V of the other — and two free-running issuers
-// let both groups reach their softmax phase together, leaving the tensor pipe idle.)
+// let both groups reach their softmax phase together, leaving the tensor pipe idle.  Starting the second issuer half a period late
+// gave the same 1.52 ms, so the cause may be elsewhere; not understood.)
 constexpr int kF2Threads = 64 + 256;
 constexpr int kF2Stages = 6;
 constexpr uint32_t kF2S = 0, kF2Q = 64, kF2O = 128, kF2Group = 256;
