@@ -346,6 +346,23 @@ def test_attention_tcgen05_wide_heads(S, N, C, qscale):
         assert r < 1.5e-2, (name, r)
 
 
+@pytest.mark.parametrize("env", [{"HDIFF_CONV_MMA2": "0", "HDIFF_CONV_STAGE": "0"}, {"HDIFF_CONV_MMA2": "1"}, {"HDIFF_CONV_MMA2": "2"},
+                                 {"HDIFF_CONV_TXM_OFF": "1"}, {"HDIFF_CONV_WRES": "1"}, {"HDIFF_WGRAD_HALO_OFF": "1"}],
+                         ids=lambda e: ",".join(f"{k[6:]}={v}" for k, v in e.items()))
+def test_conv_alternate_kernel_modes(env):
+    """The kernel modes that are not the default for a shape (one / two MMA issuers, direct-store epilogue, no shifted
+    operands, resident weights, classic wgrad) are chosen through environment switches read once per process: run the
+    convolution / wgrad parity cases again in a child process under each of them."""
+    import os
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "(test_conv_forward or wgrad) and bf16_tc"], env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_embedding_path_and_packing_kernels():
     dev = torch.device("cuda")
     ops, emu = _ops(), EmuOps()
