@@ -41,6 +41,7 @@ PROTOTYPES = {
     "hd_pad_nchw": [P, I, P, I, L, P],
     "hd_probe_shift": [P, P, P, I, I, P],
     "hd_conv_dbg_read": [P],
+    "hd_conv_tc_stats_staged": [I, I, I, I, I, I, I, I],
     "hd_probe_queue": [P, P, I, I, I, I, I, P, P],
     "hd_probe_pair": [P, P, P, I, I, I, I, P, I, I, I, I, I, P],
     "hd_conv_tc_supported": [I, I, I, I, I, I, I, I],
@@ -55,7 +56,7 @@ PROTOTYPES = {
     "hd_attn_bwd_wide_tc": [P, P, P, P, P, P, I, I, I, P],
     "hd_attn_bwd_tc_supported": [I, I],
 }
-NON_STATUS = {"hd_conv_tc_supported", "hd_wgrad_tc_supported", "hd_attn_tc_supported", "hd_attn_bwd_tc_supported", "hd_attn_wide_tc_supported",
+NON_STATUS = {"hd_conv_tc_supported", "hd_conv_tc_stats_staged", "hd_wgrad_tc_supported", "hd_attn_tc_supported", "hd_attn_bwd_tc_supported", "hd_attn_wide_tc_supported",
               "hd_wgrad_tc_workspace"}
 
 _lib = None

@@ -57,6 +57,7 @@ struct ConvTcParams {
     int mma2;                        // two MMA-issuing warps: 1 = alternate tiles (one accumulator each), 2 = both work on every stage,
                                      // each on half of its K slices into its own PARTIAL accumulator (column offset 128; NT <= 128);
                                      // the epilogue adds the two partials
+    int contig;                      // each CTA walks one contiguous range of tiles instead of striding over the grid
     int dbg;                         // timing experiments only (HDIFF_CONV_DBG): 1 = epilogue does no work, 2 = producers load nothing
     int nprod;                       // issuing threads in use (<= stages: a producer must never be two ring laps ahead,
                                      // the parity wait on `empty` cannot tell 0 completed phases from 2)
@@ -108,6 +109,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int total_tiles = p.m_tiles * p.n_tiles;
+    // tiles of this CTA: strided over the grid, or (p.contig) one contiguous range — then a CTA stays inside one image for
+    // ~100 tiles, which the staged statistics need (one flush of fp64 atomics per image change)
+    int t_begin = blockIdx.x, t_end = total_tiles, t_step = gridDim.x;
+    if (p.contig) {
+        const int per = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+        t_begin = blockIdx.x * per; t_end = t_begin + per < total_tiles ? t_begin + per : total_tiles; t_step = 1;
+    }
 
     if (warp == 0 || warp >= kFirstExtraProducer) {
         const int prod = warp == 0 ? 0 : warp - kFirstExtraProducer + 1;   // which share of the K blocks this warp's elected thread issues
@@ -120,7 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int kb = 0; kb < p.kb_w; ++kb)
                         tma_load_2d(wres_buf + (size_t)(nt * p.kb_w + kb) * b_bytes, &mapB, wfull, kb * 64, nt * p.NT);
             }
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = t_begin; tile < t_end; tile += t_step) {
                 const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
                 const int tx_i = m_tile % p.tiles_x; const int r = m_tile / p.tiles_x;
                 const int ty_i = r % p.tiles_y; const int n = r / p.tiles_y;
@@ -187,7 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint32_t wres_lo = umma_desc_lo(smem_u32(wres_buf));
             const uint32_t bstep = p.wres ? (uint32_t)per_row * b16 : b16;         // between the B tiles of two tap columns (txm)
             uint32_t a_lo = ring_lo;                     // A operand of the current stage
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
                 const int acc = it & 1;
                 if (p.mma2 == 2) {
                     // both issuers, every stage: K slices k = me, me + 2 of each operand pair into partial accumulator `me`
@@ -276,8 +284,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_arrive_expect_tx(&res_full[buf], kABytes);
             tma_load_5d(stage_buf + buf * kABytes, &mapRes, &res_full[buf], j0 - py * cv_w, txi * p.TW, py, tyi * p.TH, nn);
         };
-        if (kRes && p.stage_out && etid == 0 && (int)blockIdx.x < total_tiles) res_load(blockIdx.x, 0, 0);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        if (kRes && p.stage_out && etid == 0 && t_begin < t_end) res_load(t_begin, 0, 0);
+        // staged epilogue + statistics (Cout == 64: one block per tile): per-channel (sum, sum of squares) of the STORED bf16
+        // values are read back out of the staged tile; every warp keeps the sums of its 16 pixel rows in registers (lane:
+        // channels 2 lane, 2 lane + 1) across this CTA's consecutive tiles of one image and adds them to p.chan_sums (fp64
+        // atomics) when the image changes — a CTA walks a contiguous range of tiles, so that is once or twice per launch
+        const bool sstat = p.stage_out && p.chan_sums != nullptr;
+        int n_prev = -1;
+        float st_s0 = 0.f, st_q0 = 0.f, st_s1 = 0.f, st_q1 = 0.f;
+        auto stat_flush = [&](int nn) {
+            double* d = p.chan_sums + ((long long)nn * p.Cout + 2 * lane) * 2;
+            atomicAdd(d, (double)st_s0); atomicAdd(d + 1, (double)st_q0); atomicAdd(d + 2, (double)st_s1); atomicAdd(d + 3, (double)st_q1);
+            st_s0 = st_q0 = st_s1 = st_q1 = 0.f;
+        };
+        for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
             const int acc = it & 1;
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int tx_i = m_tile % p.tiles_x; const int r = m_tile / p.tiles_x;
@@ -301,11 +321,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 return a;
             };
             if (it == 0 && etid < p.NT) add_t[etid] = addend_load(tile);
-            const bool has_next = tile + (int)gridDim.x < total_tiles;
+            const bool has_next = tile + t_step < t_end;
             float a_next = 0.f;
-            if (has_next) a_next = addend_load(tile + gridDim.x);
+            if (has_next) a_next = addend_load(tile + t_step);
             if (kStats) for (int c = etid; c < 2 * p.NT; c += 32 * kEpiWarps) stat_s[acc * 512 + c] = 0.f;
             asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps only: this tile's addend is staged
+            if (sstat && n != n_prev) {
+                if (n_prev >= 0) stat_flush(n_prev);
+                n_prev = n;
+            }
             // element offset of this thread's pixel for output-channel 0 of each parity (P_out == 2 stores the four
             // parities of the transposed convolution through the 2x2 view); hoisted out of the chunk loop
             const long long pix1 = (((long long)n * p.H + y) * p.W + x) * p.Cout;
@@ -411,6 +435,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             vb[i] = __float_as_uint(__uint_as_float(vb[i]) + __uint_as_float(wb[i]));
                         }
                     }
+                    if (c + 64 >= p.NT) {               // last TMEM read of the tile: hand the accumulator back to the MMA issuers now,
+                        tc_fence_before();              // not after the staging, the barrier and the statistics below
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                    }
                     uint8_t* sbuf = stage_buf + (sb & 1) * kABytes;
                     if (kRes) mbar_wait(&res_full[sb & 1], (sb >> 1) & 1);
                     stage_emit(va, c, sbuf + row * 128, half * 2, nullptr);
@@ -428,8 +457,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         bulk_commit_group();
                         if (kRes) {      // the other buffer is free (its store was read out before the barrier): fetch the next block
                             if (c + 64 < p.NT) res_load(tile, (c - half * 16) / 64 + 1, (sb + 1) & 1);
-                            else if (has_next) res_load(tile + gridDim.x, 0, (sb + 1) & 1);
+                            else if (has_next) res_load(tile + t_step, 0, (sb + 1) & 1);
                         }
+                    }
+                    if (sstat) {         // this warp: 16 of the 128 staged pixel rows; lane: channels 2 lane, 2 lane + 1 of the block
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f, s2 = 0.f, s3 = 0.f, q2 = 0.f, q3 = 0.f;
+                        const int w8 = warp - 2;
+                        int rows_ok = (p.H - ty_i * p.TH) * p.TW;        // rows past the image are not stored
+                        if (rows_ok > 128) rows_ok = 128;
+                        const uint8_t* col = sbuf + (lane & 3) * 4;
+                        const uint32_t ch16 = (uint32_t)lane >> 2;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {                // two independent chains
+                            const int r = w8 * 16 + i;
+                            uint32_t wa = 0, wb = 0;
+                            if (r < rows_ok) wa = *reinterpret_cast<const uint32_t*>(col + r * 128 + ((ch16 ^ (r & 7)) << 4));
+                            if (r + 1 < rows_ok) wb = *reinterpret_cast<const uint32_t*>(col + (r + 1) * 128 + ((ch16 ^ ((r + 1) & 7)) << 4));
+                            const float a0 = __uint_as_float(wa << 16), a1 = __uint_as_float(wa & 0xFFFF0000u);
+                            const float b0 = __uint_as_float(wb << 16), b1 = __uint_as_float(wb & 0xFFFF0000u);
+                            s0 += a0; q0 = fmaf(a0, a0, q0); s1 += a1; q1 = fmaf(a1, a1, q1);
+                            s2 += b0; q2 = fmaf(b0, b0, q2); s3 += b1; q3 = fmaf(b1, b1, q3);
+                        }
+                        st_s0 += s0 + s2; st_q0 += q0 + q2; st_s1 += s1 + s3; st_q1 += q1 + q3;
                     }
                     ++sb;
                 }
@@ -524,9 +573,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (!p.stage_out) {                      // (the staged epilogue released the accumulator after its last TMEM load)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
             if (has_next && etid < p.NT) addend[(acc ^ 1) * 256 + etid] = a_next;     // visible after the next iteration's barrier
             if (kStats) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");          // every warp's contribution to this tile is in shared memory
@@ -534,6 +585,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     atomicAdd(p.chan_sums + ((long long)n * p.Cout + n_tile * p.NT) * 2 + c, (double)stat_s[acc * 512 + c]);
             }
         }
+        if (sstat && n_prev >= 0) stat_flush(n_prev);
         if (p.stage_out && etid == 0) bulk_wait_group0();           // shared memory must outlive the last tensor store
     }
     tc_fence_before();
@@ -558,6 +610,58 @@ bool conv_geometry(int H, int W, int* TH, int* TW) {
     int th = 128 / tw;
     if (th > H) return false;
     *TH = th; *TW = tw;
+    return true;
+}
+
+
+// Shared-memory plan and kernel modes of a launch (p.N .. p.kblocks, p.NT, p.kb_w already set).  Returns false when nothing fits.
+static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out, int ksize, int out_nchw_c, bool chan_sums,
+                      bool allow_stage) {
+    (void)P_out;
+    // Shared-memory plan.  Options, each dropped when the ring would get too short:
+        //   txm   shifted-operand mode: 3x3, a tile is one 128-pixel row segment (needs >= 3 stages)
+        //   wres  resident weights: the packed weight matrix fits in 96 KB
+        //   stage staged tensor-store epilogue (2 x 16 KB)
+        static const bool txm_off = getenv("HDIFF_CONV_TXM_OFF") != nullptr;
+        static const bool wres_on = getenv("HDIFF_CONV_WRES") != nullptr;    // measured: no gain (the operand fetch of the MMAs bounds
+                                                                             // the kernel, not the TMA fill), so off by default
+        static const int stage_env = getenv("HDIFF_CONV_STAGE") ? atoi(getenv("HDIFF_CONV_STAGE")) : 2;   // 0 off, 1 1x1 only, 2 every eligible conv
+        const int budget = 200 * 1024;
+        const long long wbytes = (long long)CoutL * p.kb_w * 128;
+        const bool want_txm = !txm_off && ksize == 3 && p.TH == 1 && p.TW == 128;
+        const bool want_wres = wres_on && wbytes <= 96 * 1024;
+        const bool want_stage = allow_stage && out_nchw_c == 0 && p.NT % 64 == 0 && Cout % 64 == 0 &&
+                                (stage_env == 2 || (stage_env == 1 && ksize == 1));
+        const int txm_a_tx = (p.TW + 2) * 128, txm_a_slot = (txm_a_tx + 1023) / 1024 * 1024;
+        auto stages_of = [&](bool txm, bool wres, bool stage) {
+            const int sbytes = (txm ? txm_a_slot : kABytes) + (wres ? 0 : (txm ? 3 : 1) * p.NT * 128);
+            const long long avail = budget - (stage ? 2 * kABytes : 0) - (wres ? wbytes : 0);
+            return avail <= 0 ? 0 : (int)(avail / sbytes);
+        };
+        bool txm = false, wres = false, stage = false, found = false;
+        for (int t = want_txm ? 1 : 0; t >= 0 && !found; --t)
+            for (int w = want_wres ? 1 : 0; w >= 0 && !found; --w)
+                for (int g = want_stage ? 1 : 0; g >= 0 && !found; --g)
+                    if (stages_of(t, w, g) >= (t ? 3 : 2)) { txm = t; wres = w; stage = g; found = true; }
+        if (!found) return false;
+        p.txm = txm; p.wres = wres; p.stage_out = stage;
+        static const int dbg = getenv("HDIFF_CONV_DBG") ? atoi(getenv("HDIFF_CONV_DBG")) : 0;
+        p.dbg = dbg;
+        static const int contig_env = getenv("HDIFF_CONV_CONTIG") ? atoi(getenv("HDIFF_CONV_CONTIG")) : -1;
+        p.contig = contig_env >= 0 ? contig_env : (chan_sums && stage ? 1 : 0);
+        // second issuer.  Mode 1 (alternate tiles): a gain where the issuing thread is the bottleneck (64->64: 0.201 -> 0.178 ms),
+        // a small loss at N = 128 (+5 %: the watcher's arrive delays the release of a stage).  Mode 2 (both issuers on every
+        // stage, partial accumulators): the same at 64->64, no loss at N = 128 (ring-fill bound: 0.139 ms either way) and a
+        // further gain on tiles with many stages (128+64 -> 64: 0.473 -> 0.438 ms); on 1x1 layers (one stage per tile) mode 1 is the better one.  HDIFF_CONV_MMA2=0/1/2 forces a mode.
+        static const int mma2_env = getenv("HDIFF_CONV_MMA2") ? atoi(getenv("HDIFF_CONV_MMA2")) : -1;
+        int mode = 0;                                   // by shape, from per-layer timings inside a training step
+        if (p.NT <= 64) mode = ksize == 1 ? 1 : 2;
+        else if (p.NT <= 128 && ksize == 3) mode = (p.txm && P_in == 1) ? 0 : 2;
+        p.mma2 = mma2_env >= 0 ? mma2_env : mode;
+        if (p.mma2 == 2 && (p.NT > 128 || p.wres)) p.mma2 = p.NT <= 64 ? 1 : 0;
+        p.a_slot = txm ? txm_a_slot : kABytes; p.a_tx = txm ? txm_a_tx : kABytes;
+        if (txm) p.kblocks = 3 * P_in * p.nchunk_c;       // stages per tile: one per (tap row, parity row, chunk)
+        p.stages = stages_of(txm, wres, stage); if (p.stages > kMaxStages) p.stages = kMaxStages;
     return true;
 }
 
@@ -636,50 +740,9 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     p.kblocks = ksize * ksize * P_in * p.nchunk_c;
     const int CinL = (C0 + C1) * P_in * P_in;
     p.kb_w = p.kblocks;
-    {   // Shared-memory plan.  Options, each dropped when the ring would get too short:
-        //   txm   shifted-operand mode: 3x3, a tile is one 128-pixel row segment (needs >= 3 stages)
-        //   wres  resident weights: the packed weight matrix fits in 96 KB
-        //   stage staged tensor-store epilogue (2 x 16 KB)
-        static const bool txm_off = getenv("HDIFF_CONV_TXM_OFF") != nullptr;
-        static const bool wres_on = getenv("HDIFF_CONV_WRES") != nullptr;    // measured: no gain (the operand fetch of the MMAs bounds
-                                                                             // the kernel, not the TMA fill), so off by default
-        static const int stage_env = getenv("HDIFF_CONV_STAGE") ? atoi(getenv("HDIFF_CONV_STAGE")) : 2;   // 0 off, 1 1x1 only, 2 every eligible conv
-        const int budget = 200 * 1024;
-        const long long wbytes = (long long)CoutL * p.kb_w * 128;
-        const bool want_txm = !txm_off && ksize == 3 && p.TH == 1 && p.TW == 128;
-        const bool want_wres = wres_on && wbytes <= 96 * 1024;
-        const bool want_stage = out_nchw_c == 0 && !chan_sums && p.NT % 64 == 0 && Cout % 64 == 0 &&
-                                (stage_env == 2 || (stage_env == 1 && ksize == 1));
-        const int txm_a_tx = (p.TW + 2) * 128, txm_a_slot = (txm_a_tx + 1023) / 1024 * 1024;
-        auto stages_of = [&](bool txm, bool wres, bool stage) {
-            const int sbytes = (txm ? txm_a_slot : kABytes) + (wres ? 0 : (txm ? 3 : 1) * p.NT * 128);
-            const long long avail = budget - (stage ? 2 * kABytes : 0) - (wres ? wbytes : 0);
-            return avail <= 0 ? 0 : (int)(avail / sbytes);
-        };
-        bool txm = false, wres = false, stage = false, found = false;
-        for (int t = want_txm ? 1 : 0; t >= 0 && !found; --t)
-            for (int w = want_wres ? 1 : 0; w >= 0 && !found; --w)
-                for (int g = want_stage ? 1 : 0; g >= 0 && !found; --g)
-                    if (stages_of(t, w, g) >= (t ? 3 : 2)) { txm = t; wres = w; stage = g; found = true; }
-        HD_REQUIRE(found);
-        p.txm = txm; p.wres = wres; p.stage_out = stage;
-        static const int dbg = getenv("HDIFF_CONV_DBG") ? atoi(getenv("HDIFF_CONV_DBG")) : 0;
-        p.dbg = dbg;
-        // second issuer.  Mode 1 (alternate tiles): a gain where the issuing thread is the bottleneck (64->64: 0.201 -> 0.178 ms),
-        // a small loss at N = 128 (+5 %: the watcher's arrive delays the release of a stage).  Mode 2 (both issuers on every
-        // stage, partial accumulators): the same at 64->64, no loss at N = 128 (ring-fill bound: 0.139 ms either way) and a
-        // further gain on tiles with many stages (128+64 -> 64: 0.473 -> 0.438 ms); inside a training step it is slower than mode 1
-        // on the 3-stage 64->64 tiles and on 1x1 layers.  HDIFF_CONV_MMA2=0/1/2 forces a mode.
-        static const int mma2_env = getenv("HDIFF_CONV_MMA2") ? atoi(getenv("HDIFF_CONV_MMA2")) : -1;
-        int mode = 0;                                   // by shape, from per-layer timings inside a training step
-        if (p.NT <= 64) mode = (ksize == 1 || p.kblocks <= 3) ? 1 : 2;
-        else if (p.NT <= 128 && ksize == 3) mode = (p.txm && P_in == 1) ? 0 : 2;
-        p.mma2 = mma2_env >= 0 ? mma2_env : mode;
-        if (p.mma2 == 2 && (p.NT > 128 || p.wres || chan_sums)) p.mma2 = p.NT <= 64 ? 1 : 0;
-        p.a_slot = txm ? txm_a_slot : kABytes; p.a_tx = txm ? txm_a_tx : kABytes;
-        if (txm) p.kblocks = 3 * P_in * p.nchunk_c;       // stages per tile: one per (tap row, parity row, chunk)
-        p.stages = stages_of(txm, wres, stage); if (p.stages > kMaxStages) p.stages = kMaxStages;
-    }
+    // statistics in the staged epilogue handle one 64-channel block per tile; other widths with `chan_sums` take the direct-store
+    // epilogue and its register butterfly
+    HD_REQUIRE(conv_plan(p, CoutL, Cout, P_in, P_out, ksize, out_nchw_c, chan_sums != nullptr, !chan_sums || Cout == 64));
     const int stage_bytes = p.a_slot + (p.wres ? 0 : (p.txm ? 3 : 1) * p.NT * 128);
     p.nprod = p.stages < kProducers ? p.stages : kProducers;
     p.Cout = Cout; p.P_out = P_out;
@@ -687,6 +750,7 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     p.res = (const __nv_bfloat16*)res; p.out = (__nv_bfloat16*)out;
     p.out_nchw = out_nchw_c ? (float*)out : nullptr; p.nchw_c = out_nchw_c;
     HD_REQUIRE(!chan_sums || (P_out == 1 && out_nchw_c == 0));
+
     p.chan_sums = chan_sums;
 
     CUtensorMap mA0, mA1, mB, mOut, mRes;
@@ -716,7 +780,7 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
         attr_set = true;
     }
     int grid = p.m_tiles * p.n_tiles; const int sms = hd_num_sms(); if (grid > sms) grid = sms;
-    if (chan_sums) {
+    if (chan_sums && !p.stage_out) {          // (the staged epilogue takes its statistics from the staged tile, no template flag)
         if (res) conv_tc_kernel<true, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
         else conv_tc_kernel<true, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
     } else {
@@ -732,4 +796,22 @@ extern "C" int hd_conv_dbg_read(long long* out4) {
     HD_REQUIRE(out4);
     if (cudaMemcpyFromSymbol(out4, g_conv_dbg, sizeof(long long) * 4) != cudaSuccess) { hd_set_error("cudaMemcpyFromSymbol"); return HD_ERR_CUDA; }
     return HD_OK;
+}
+
+// 1 if a launch of this shape with `chan_sums` takes the staged epilogue, where the GroupNorm statistics of the output are
+// read back out of the staged tile in shared memory (cheap); 0 if it would run the register butterfly of the direct-store
+// epilogue (measured slower than a separate hd_gn_stats pass) or the shape is not supported.
+extern "C" int hd_conv_tc_stats_staged(int C0, int C1, int P_in, int Cout, int P_out, int H, int W, int ksize) {
+    if (P_out != 1 || Cout != 64 || !hd_conv_tc_supported(C0, C1, P_in, Cout, P_out, H, W, ksize)) return 0;
+    ConvTcParams p{};
+    p.H = H; p.W = W;
+    conv_geometry(H, W, &p.TH, &p.TW);
+    const int CoutL = Cout * P_out * P_out;
+    p.NT = pick_nt(CoutL); p.n_tiles = CoutL / p.NT;
+    p.k = ksize; p.P_in = P_in;
+    p.nchunk_c = P_in == 1 ? (C0 + C1) / 64 : 2 * C0 / 64;
+    p.kblocks = ksize * ksize * P_in * p.nchunk_c;
+    p.kb_w = p.kblocks;
+    if (!conv_plan(p, CoutL, Cout, P_in, P_out, ksize, 0, true, true)) return 0;
+    return p.stage_out ? 1 : 0;
 }

@@ -25,7 +25,10 @@ from . import ops as _ops
 
 GN_GROUPS = 32
 GN_EPS = 1e-5
-CONV_EPILOGUE_STATS = os.environ.get("HDIFF_CONV_STATS", "0") == "1"
+# GroupNorm statistics out of the producing convolution's epilogue: "auto" = only where the kernel takes them from the tile it
+# has staged in shared memory for its tensor store (cheap), "1" = also through the register butterfly of the direct-store
+# epilogue (measured slower than the separate statistics pass), "0" = never.
+CONV_EPILOGUE_STATS = os.environ.get("HDIFF_CONV_STATS", "auto")
 # Weight gradients leave the dependency chain of the backward pass (nothing reads them before the optimizer / all-reduce),
 # so they CAN be issued on a second stream: the tensor-pipe-bound wgrad kernels then run under the HBM-bound GroupNorm
 # backward kernels of the next layer instead of in front of them.  Measured on B200 (cfg2, batch 32): 86.1 -> 84.9 ms per
@@ -458,11 +461,11 @@ class UNetBase(nn.Module):
         else:
             out = torch.empty((N, H * P_out, W * P_out, Cout), dtype=self.compute_dtype, device=x0.device)
         cs = None
-        # Off by default: measured on B200 the statistics epilogue costs more than the pass it saves (conv 64->64 at 256x256:
-        # 0.216 -> 0.356 ms against 0.08 ms for hd_gn_stats; 128->128 at 128x128: +0.045 ms against 0.046 ms).
-        if (want_stats and CONV_EPILOGUE_STATS and not dgrad and not out_nchw and P_out == 1
-                and self.compute_dtype == torch.bfloat16):
-            cs = self._chan_alloc(st, N, Cout)
+        if (want_stats and CONV_EPILOGUE_STATS != "0" and not dgrad and not out_nchw and not in_nchw and P_out == 1
+                and self.compute_dtype == torch.bfloat16 and ops.use_tc):
+            C0, C1 = x0.shape[-1], 0 if x1 is None else x1.shape[-1]
+            if CONV_EPILOGUE_STATS == "1" or ops.lib.hd_conv_tc_stats_staged(C0, C1, P_in, Cout, P_out, H, W, spec.k):
+                cs = self._chan_alloc(st, N, Cout)
         got = ops.conv(x0, x1, P_in, self._wv(st, spec, dgrad), None if dgrad else self._bv(st, spec), emb, res, out, P_out,
                        N, H, W, spec.k, in_nchw=in_nchw, out_nchw=out_nchw, alg_frac=spec.alg_frac,
                        Cout_pad=Cout if out_nchw and Cout != spec.real_cout else None, chan_sums=cs)

@@ -133,6 +133,9 @@ int hd_sampler_step(float* x, const float* eps_c, const float* eps_u, const floa
                     const int* step_ptr, int last_step_clip, int* nan_flag, int64_t n, hd_stream_t stream);
 int hd_add_int(int* p, int delta, hd_stream_t stream);
 
+/* 1 if hd_conv_tc with `chan_sums` would take the staged epilogue for this shape (statistics read back out of the staged
+ * tile: cheap); the host requests conv-epilogue statistics only then */
+int hd_conv_tc_stats_staged(int C0, int C1, int P_in, int Cout, int P_out, int H, int W, int ksize);
 /* timing experiments (HDIFF_CONV_DBG=4): (clock64, globaltimer ns) at the start / end of CTA 0 of the last hd_conv_tc launch */
 int hd_conv_dbg_read(long long* out4);
 /* ---- hardware probe (scripts/probe_shift.py): tcgen05 A operand starting at an arbitrary 128-byte row of a swizzled box ---- */
