@@ -6,6 +6,8 @@ Reference followed (paths relative to the reference repository):
   GaussianDiffusionTrainer     DiffusionFreeGuidence/DiffusionCondition.py:19-46  (uncond twin diffusion/Diffusion.py:304-314)
   GaussianDiffusionSampler     DiffusionFreeGuidence/DiffusionCondition.py:49-98  (uncond twin diffusion/Diffusion.py:351-368)
 
+  DDIM (eta = 0) with guidance  diffusion/Diffusion.py:241-269 (the hybrid sampler's `ddim=True` branch), SURVEY §8(f) rank 2
+
 Differences kept deliberately: the per-step `print` (:88) is dropped and the per-step NaN
 assertion (:96, a device->host sync) becomes a device flag checked once after the last step.
 """
@@ -38,6 +40,7 @@ def schedule_tables(beta_1, beta_T, T):
         "coeff1": coeff1,
         "coeff2": coeff1 * (1. - alphas) / torch.sqrt(1. - alphas_bar),
         "posterior_var": betas * (1. - alphas_bar_prev) / (1. - alphas_bar),
+        "alphas_bar": alphas_bar,
     }
 
 
@@ -105,6 +108,31 @@ class GaussianDiffusionSampler(nn.Module):
         var = torch.cat([tab["posterior_var"][1:2], tab["betas"][1:]])          # DiffusionCondition.py:74
         coef = torch.stack([tab["coeff1"].float(), tab["coeff2"].float(), torch.sqrt(var.float())], dim=1).contiguous()
         self.register_buffer('_coef', coef, persistent=False)                    # [T][3] fp32
+        self.register_buffer('alphas_bar', tab["alphas_bar"])
+        self._ddim = {}                                                          # ddim_step -> (coef table [n][3] fp32, stride)
+
+    def ddim_tables(self, ddim_step):
+        """Coefficients of the deterministic DDIM update of diffusion/Diffusion.py:241-269 (eta = 0):
+            seq = range(0, T, T // ddim_step), visited from its end; at step i (previous entry j, -1 before the first):
+            at = alphas_bar[i + 1], at_next = alphas_bar[j + 1]                      (:251-252, the reference indexes at t + 1)
+            y0 = (y_t - eps sqrt(1 - at)) / sqrt(at);  y_{next} = sqrt(at_next) y0 + sqrt(1 - at_next) eps   (:261-265, c1 = 0)
+        which is the linear update  y_next = k1 y_t - k2 eps  that hd_sampler_step applies, with
+            k1 = sqrt(at_next) / sqrt(at),   k2 = sqrt(at_next) sqrt(1 - at) / sqrt(at) - sqrt(1 - at_next)
+        and no noise term.  Returns (table [len(seq)][3] fp32 in seq order, stride); the reference hard-codes 1000 for T."""
+        ddim_step = int(ddim_step)
+        if ddim_step not in self._ddim:
+            stride = int(self.T / ddim_step)
+            assert stride >= 1 and ddim_step >= 1
+            seq = list(range(0, self.T, stride))
+            seq_next = [-1] + seq[:-1]
+            assert seq[-1] + 1 < self.T, "alphas_bar is read at t + 1 (Diffusion.py:251)"
+            ab = self.alphas_bar
+            at = ab[torch.tensor([i + 1 for i in seq], device=ab.device)].float()            # extract(...).float()
+            an = ab[torch.tensor([j + 1 for j in seq_next], device=ab.device)].float()
+            k1 = an.sqrt() / at.sqrt()
+            k2 = an.sqrt() * (1 - at).sqrt() / at.sqrt() - (1 - an).sqrt()
+            self._ddim[ddim_step] = (torch.stack([k1, k2, torch.zeros_like(k1)], dim=1).contiguous(), stride)
+        return self._ddim[ddim_step]
 
     def predict_xt_prev_mean_from_eps(self, x_t, t, eps):
         assert x_t.shape == eps.shape
@@ -120,12 +148,13 @@ class GaussianDiffusionSampler(nn.Module):
 
     use_cuda_graph = True      # capture one time step (2B-batch UNet forward + fused update) and replay it T-1 times
 
-    def _one_step(self, x, labels, step, nan_flag):
+    def _one_step(self, x, labels, step, nan_flag, coef=None, stride=1):
         """One ancestral step, in place on x.  The time index lives in device memory (`step`), so the same launch
-        sequence serves every t (DiffusionCondition.py:86-95 with the per-step print / host NaN check removed)."""
+        sequence serves every t (DiffusionCondition.py:86-95 with the per-step print / host NaN check removed).
+        `coef` / `stride`: another update table indexed by `step`, with the network evaluated at t = step * stride (DDIM)."""
         ops = _ops.get()
         B = x.shape[0]
-        t = step.to(torch.int64).expand(B).contiguous()
+        t = (step.to(torch.int64) * stride).expand(B).contiguous()
         if labels is None:
             eps_c, eps_u = self.model(x, t), None
         else:
@@ -134,37 +163,50 @@ class GaussianDiffusionSampler(nn.Module):
         eps_c = eps_c.contiguous()
         assert eps_c.shape == x.shape
         z = torch.randn_like(x)                  # ignored by the kernel at t == 0 (the reference adds no noise there)
-        ops.sampler_step(x, eps_c, eps_u, z, self.w, self._coef, step, True, nan_flag)
+        ops.sampler_step(x, eps_c, eps_u, z, self.w, self._coef if coef is None else coef, step, True, nan_flag)
         ops.add_int(step, -1)
 
-    def run_steps(self, x, labels, step, nan_flag, n_steps):
+    def run_steps(self, x, labels, step, nan_flag, n_steps, coef=None, stride=1):
         """Advance `n_steps` time steps starting at the index held in `step` (bench.py times a bounded number of steps)."""
         frozen = self.model.frozen_weights() if hasattr(self.model, "frozen_weights") else _Null()
         graphable = self.use_cuda_graph and x.is_cuda and n_steps > 2 and hasattr(self.model, "frozen_weights")
         with torch.no_grad(), frozen:
             if not graphable:
                 for _ in range(n_steps):
-                    self._one_step(x, labels, step, nan_flag)
+                    self._one_step(x, labels, step, nan_flag, coef, stride)
                 return
             # the captured step is bound to these buffers; callers that keep them (bench.py, chunked sampling) reuse it
-            key = (x.data_ptr(), tuple(x.shape), None if labels is None else labels.data_ptr(), step.data_ptr(), nan_flag.data_ptr())
+            key = (x.data_ptr(), tuple(x.shape), None if labels is None else labels.data_ptr(), step.data_ptr(), nan_flag.data_ptr(),
+                   None if coef is None else coef.data_ptr(), stride)
             cached = getattr(self, "_graph", None)
             if cached is None or cached[0] != key:
-                self._one_step(x, labels, step, nan_flag)    # eager: also initialises every lazily built state
+                self._one_step(x, labels, step, nan_flag, coef, stride)    # eager: also initialises every lazily built state
                 n_steps -= 1
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    self._one_step(x, labels, step, nan_flag)
+                    self._one_step(x, labels, step, nan_flag, coef, stride)
                 self._graph = cached = (key, graph)
             for _ in range(n_steps):
                 cached[1].replay()
 
-    def forward(self, x_T, labels=None):
+    def forward(self, x_T, labels=None, ddim=False, ddim_step=None):
+        """ddim=True: the deterministic DDIM sampler of the hybrid pipeline (diffusion/Diffusion.py:241-269, eta = 0) over
+        `ddim_step` of the T time steps, with the same classifier-free guidance (its `unconditional_guidance_scale` is
+        1 + w) — ten times fewer network evaluations at ddim_step = 100."""
         assert x_T.dtype == torch.float32
         dev = x_T.device
         x = x_T.clone().contiguous()
-        step = torch.full((1,), self.T - 1, dtype=torch.int32, device=dev)
         nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        if ddim:
+            coef, stride = self.ddim_tables(self.T if ddim_step is None else ddim_step)
+            coef = coef.to(dev)
+            n = coef.shape[0]
+            step = torch.full((1,), n - 1, dtype=torch.int32, device=dev)
+            self.run_steps(x, labels, step, nan_flag, n, coef, stride)
+            self._graph = None
+            assert int(nan_flag.item()) == 0, "nan in tensor."
+            return x
+        step = torch.full((1,), self.T - 1, dtype=torch.int32, device=dev)
         self.run_steps(x, labels, step, nan_flag, self.T)
         self._graph = None                       # bound to this call's buffers
         assert int(nan_flag.item()) == 0, "nan in tensor."

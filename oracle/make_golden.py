@@ -165,6 +165,39 @@ def unet_tiny():
     torch.save(out, os.path.join(OUT, "unet_tiny.pt"))
 
 
+class DdimDummy(nn.Module):
+    """Deterministic stand-in for the hybrid pipeline's network in the DDIM fixture: input = cat(conditioning image, y_t)
+    (diffusion/Diffusion.py:253).  The reference calls it as model(input, t) and, for guidance, model(input, t,
+    context_zero=True) (:254,258): the two calls are told apart by the keyword being passed at all."""
+
+    def forward(self, inp, t, context_zero=None):
+        y = inp[:, 3:]
+        tt = (t.float() / 1000.).view(-1, 1, 1, 1)
+        return ddim_dummy_eps(y, tt, cond=context_zero is None)
+
+
+def ddim_dummy_eps(y, tt, cond):
+    """Roughly 'the noise is most of y_t', so that the trajectory stays inside (-1, 1) and the final clip hides nothing."""
+    return 0.9 * y + 0.1 * torch.tanh(y) + 0.05 * tt if cond else 0.8 * y - 0.05 * tt
+
+
+def ddim_reference():
+    """The hybrid sampler's DDIM branch (diffusion/Diffusion.py:241-269), run from the reference class itself."""
+    Sampler = ref_loader.hybrid_sampler_class()
+    out = {"beta_1": 1e-4, "beta_T": 0.02, "T": 1000, "runs": []}
+    sa = Sampler(DdimDummy(), 1e-4, 0.02, 1000)
+    torch.manual_seed(30)
+    img = torch.randint(0, 256, (2, 3, 8, 8)).float()
+    for seed, scale, steps in ((31, 1, 100), (32, 1.8, 100), (33, 2.5, 20)):
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            y0 = sa(img, ddim=True, unconditional_guidance_scale=scale, ddim_step=steps).clone()
+        torch.manual_seed(seed)
+        xT = torch.randn_like(img)               # the reference's first draw (:243)
+        out["runs"].append({"seed": seed, "scale": scale, "ddim_step": steps, "xT": xT, "y0": y0})
+    torch.save(out, os.path.join(OUT, "ddim_reference.pt"))
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -172,5 +205,6 @@ if __name__ == "__main__":
     diffusion_identity()
     blocks()
     unet_tiny()
+    ddim_reference()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -153,3 +153,23 @@ def assemble_unet(T, ch, ch_mult, attn, num_res_blocks, dropout, num_labels=None
         return layer(h, temb, cemb)
 
     return RefUNet()
+
+
+def hybrid_sampler_class():
+    """`GaussianDiffusionSampler` of diffusion/Diffusion.py:181-269 (the hybrid pipeline's sampler, with the DDIM branch
+    :241-269) and its `extract` (:16-23).  The module itself cannot be imported here (it needs kornia / lpips and reaches for
+    torch.hub + CUDA in another class), so the two definitions are cut out of the unmodified source by AST and executed on
+    their own."""
+    if "hybrid" not in _cache:
+        import ast
+        import torch.nn.functional as F
+        path = os.path.join(REF_ROOT, "diffusion", "Diffusion.py")
+        with open(path, "r") as f:
+            tree = ast.parse(f.read())
+        keep = [n for n in tree.body if (isinstance(n, ast.FunctionDef) and n.name == "extract")
+                or (isinstance(n, ast.ClassDef) and n.name == "GaussianDiffusionSampler")]
+        assert len(keep) == 2, [getattr(n, "name", None) for n in keep]
+        ns = {"torch": torch, "nn": nn, "F": F}
+        exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+        _cache["hybrid"] = ns["GaussianDiffusionSampler"]
+    return _cache["hybrid"]

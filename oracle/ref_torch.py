@@ -294,6 +294,40 @@ class GaussianDiffusionSampler(nn.Module):
         return torch.clip(x_t, -1, 1)
 
 
+def ddim_sample(model, beta_1, beta_T, T, x_T, labels=None, guidance_scale=1., ddim_step=100):
+    """Deterministic DDIM sampling with classifier-free guidance: the `ddim=True` branch of the hybrid sampler,
+    diffusion/Diffusion.py:241-269, restated line by line for a label-conditional network.
+
+    What differs from the reference lines, and why:
+      * the reference draws y_T itself (`randn_like(input_image)`, :243) and concatenates the conditioning image to the
+        network input (:253); here x_T is an argument and the network takes (x, t[, labels]) — SURVEY §8(f): the
+        image-conditional DynamicUNet is not on the path;
+      * the guidance pair is eps(x, t, labels) and eps(x, t, 0) (the null label), mixed exactly as :258-259;
+      * `1000` (:246-247) is written as T.
+    `c1 * randn_like` (:264-265) is kept: it multiplies by zero (eta = 0) but advances the generator as the reference does.
+    Pinned by tests/golden/ddim_reference.pt, minted from the reference class itself (oracle/make_golden.py)."""
+    alphas_bar = torch.cumprod(1. - torch.linspace(beta_1, beta_T, T).double(), dim=0).to(x_T.device)      # :188-190
+    y_t = x_T
+    step = int(T / ddim_step)                                                                                # :246-247
+    seq = range(0, T, step)
+    seq_next = [-1] + list(seq[:-1])
+    for i, j in zip(reversed(seq), reversed(seq_next)):
+        t = (torch.ones(y_t.shape[0]) * i).to(y_t.device).long()
+        next_t = (torch.ones(y_t.shape[0]) * j).to(y_t.device).long()
+        at = extract(alphas_bar, (t + 1).long(), y_t.shape)                                                  # :251
+        at_next = extract(alphas_bar, (next_t + 1).long(), y_t.shape)                                        # :252
+        eps = model(y_t, t) if labels is None else model(y_t, t, labels)                                     # :254
+        if guidance_scale != 1 and labels is not None:                                                       # :257-259
+            eps_unconditional = model(y_t, t, torch.zeros_like(labels))
+            eps = eps_unconditional + guidance_scale * (eps - eps_unconditional)
+        y0_pred = (y_t - eps * (1 - at).sqrt()) / at.sqrt()                                                  # :261
+        eta = 0
+        c1 = eta * ((1 - at / at_next) * (1 - at_next) / (1 - at)).sqrt()                                    # :263
+        c2 = ((1 - at_next) - c1 ** 2).sqrt()                                                                # :264
+        y_t = at_next.sqrt() * y0_pred + c1 * torch.randn_like(y_t) + c2 * eps                               # :265
+    return torch.clip(y_t, -1, 1)                                                                            # :267
+
+
 # --------------------------------------------------------------------------------------
 # Caller contract (TrainCondition.py:53-63, diffusion/Train.py:49-55): one training step
 # --------------------------------------------------------------------------------------

@@ -171,3 +171,20 @@ def test_bf16_schedule_with_padded_head_and_tail_vs_oracle():
         p = dict(net.named_parameters())[k]
         assert p.grad.shape == pr[k].grad.shape
         assert _close(p.grad, pr[k].grad, 5e-2, 1e-3 * gscale), (k, _rel(p.grad, pr[k].grad))
+
+
+def test_ddim_sampler_vs_reference_golden(golden_dir):
+    """GaussianDiffusionSampler(..., w)(x_T, labels, ddim=True, ddim_step=n): the hybrid sampler's DDIM branch
+    (diffusion/Diffusion.py:241-269, eta = 0, guidance scale 1 + w) as one linear update per step through hd_sampler_step."""
+    from tests.test_oracle import _DdimModel
+    g = torch.load(os.path.join(golden_dir, "ddim_reference.pt"))
+    for run in g["runs"]:
+        sa = GaussianDiffusionSampler(_DdimModel(), g["beta_1"], g["beta_T"], g["T"], w=run["scale"] - 1.)
+        sa.model.cfg_batched = False                 # the stand-in tells its two branches apart by whole-batch labels
+        y0 = sa(run["xT"], torch.tensor([1, 2]), ddim=True, ddim_step=run["ddim_step"])
+        assert torch.allclose(y0, run["y0"], atol=2e-5), float((y0 - run["y0"]).abs().max())
+    # the table itself: seq order, t + 1 indexing, no noise term
+    coef, stride = sa.ddim_tables(20)
+    assert stride == 50 and coef.shape == (20, 3) and float(coef[:, 2].abs().max()) == 0.0
+    ab = sa.alphas_bar
+    assert abs(float(coef[0, 0]) - float((ab[0].float().sqrt() / ab[1].float().sqrt()))) < 1e-7

@@ -278,3 +278,32 @@ def test_flat_adamw_matches_clip_grad_norm_plus_torch_adamw():
         if k.endswith("cond_proj.1.weight") or k.endswith("cond_proj.1.bias"):
             continue            # never used by the unconditional model: torch skips them (grad None), the flat step only decays them
         assert torch.allclose(pa[k].detach(), pb[k].detach(), rtol=1e-4, atol=2e-6), (k, float((pa[k] - pb[k]).abs().max()))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 0.1)])
+def test_ddim_cfg_sampler_vs_oracle(golden_dir, dtype, tol):
+    """DDIM (eta = 0) with classifier-free guidance on the CUDA path (CUDA graph replay of the step) against the oracle's
+    restatement of diffusion/Diffusion.py:241-269, same network weights, same x_T; and against the reference fixture through
+    the fixture's stand-in network."""
+    from hdiff_b200.DiffusionFreeGuidence.DiffusionCondition import GaussianDiffusionSampler
+    from tests.test_oracle import _DdimModel
+    dev = torch.device("cuda")
+    g = _load(golden_dir, "unet_tiny.pt")
+    net, ref = _nets(g["cfg"], 10, dtype, dev, sd=g["sd"])
+    net.eval(); ref.eval()
+    xT = g["sampler"]["xT"].to(dev)
+    lab = g["sampler"]["labels"].to(dev)
+    T = g["cfg"]["T"]                                # the time-embedding table of the fixture's network has T rows
+    smp = GaussianDiffusionSampler(net, 1e-4, 0.02, T, w=0.8).to(dev)
+    x0 = smp(xT, lab, ddim=True, ddim_step=10)
+    with torch.no_grad():
+        r0 = R.ddim_sample(ref, 1e-4, 0.02, T, xT, lab, guidance_scale=1.8, ddim_step=10)
+    assert float((x0 - r0).abs().max()) < tol, float((x0 - r0).abs().max())
+    assert float(x0.abs().max()) <= 1.0
+    if dtype == torch.float32:
+        d = _load(golden_dir, "ddim_reference.pt")
+        for run in d["runs"]:
+            sa = GaussianDiffusionSampler(_DdimModel(), d["beta_1"], d["beta_T"], d["T"], w=run["scale"] - 1.).to(dev)
+            sa.model.cfg_batched = False
+            y0 = sa(run["xT"].to(dev), torch.tensor([1, 2], device=dev), ddim=True, ddim_step=run["ddim_step"])
+            assert torch.allclose(y0.cpu(), run["y0"], atol=3e-5), float((y0.cpu() - run["y0"]).abs().max())

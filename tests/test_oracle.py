@@ -143,3 +143,23 @@ def test_oracle_vs_live_reference_state_dict_and_forward():
     live = mc.UNet(T=50, num_labels=4, ch=32, ch_mult=[1, 2], num_res_blocks=1, dropout=0.0)
     live_keys = {k for k in live.state_dict() if ".attn." not in k}
     assert live_keys == {k for k in mine.state_dict() if ".attn." not in k}
+
+
+class _DdimModel(torch.nn.Module):
+    """The DDIM fixture's stand-in network behind the label interface: labels != 0 -> its conditional branch, 0 -> the other."""
+
+    def forward(self, x, t, labels=None):
+        from oracle.make_golden import ddim_dummy_eps
+        tt = (t.float() / 1000.).view(-1, 1, 1, 1)
+        return ddim_dummy_eps(x, tt, cond=labels is None or bool((labels != 0).all()))
+
+
+def test_ddim_restatement_matches_reference_golden(golden_dir):
+    """oracle.ddim_sample == the hybrid sampler's DDIM branch run from the reference class (diffusion/Diffusion.py:241-269)."""
+    g = torch.load(os.path.join(golden_dir, "ddim_reference.pt"))
+    for run in g["runs"]:
+        torch.manual_seed(run["seed"])
+        xT = torch.randn_like(run["xT"])
+        assert torch.equal(xT, run["xT"])
+        y0 = R.ddim_sample(_DdimModel(), g["beta_1"], g["beta_T"], g["T"], xT, torch.tensor([1, 2]), run["scale"], run["ddim_step"])
+        assert torch.allclose(y0, run["y0"], atol=2e-6), float((y0 - run["y0"]).abs().max())
