@@ -282,6 +282,9 @@ def run_ours(args):
                     "note": f"{args.sample_steps} of the {CFG2['T']} ancestral steps timed (each = one 2B-batch conditional+null UNet forward "
                             "+ fused CFG/posterior update) as replays of the step's CUDA graph (captured once during warm-up, as it is once per 1000-step "
                             "chain), extrapolated to the full chain",
+                    "ddim100_images_per_s": world * Bs / (per_step * 1e-3 * 100),
+                    "ddim_note": "the same step (same launches; another coefficient table) run as the 100-step deterministic DDIM sampler "
+                                 "of the hybrid pipeline (sampler(x_T, labels, ddim=True, ddim_step=100)); derived from the step time above",
                     "batch_per_gpu": Bs, "global_batch": world * Bs, "guidance_w": 1.8, "cuda_graph": bool(sampler.use_cuda_graph),
                     "nan_flag": int(nan_flag.item())}
     value = world * B * args.steps / (ms * 1e-3)
