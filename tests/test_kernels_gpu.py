@@ -49,6 +49,10 @@ CONV_CASES = [
     ("3x3_rowseg_n192", 64, 0, 1, 192, 1, 1, 2, 256, 3, False, False),
     # several tiles per persistent CTA with a 3-stage ring (fewer stages than TMA-issuing warps)
     ("3x3_rowseg_128_128_many_tiles", 128, 0, 1, 128, 1, 8, 64, 128, 3, True, True),
+    # 64 channels, several tiles per CTA, image boundaries inside a CTA's tile range (41 rows per image, ranges of 2): the
+    # staged-epilogue statistics flush when the image changes
+    ("3x3_rowseg_64_64_many_images", 64, 0, 1, 64, 1, 6, 41, 128, 3, True, True),
+    ("1x1_64_64_many_images", 64, 64, 1, 64, 1, 5, 37, 128, 1, False, True),
 ]
 
 
