@@ -25,8 +25,8 @@ PROTOTYPES = {
     "hd_scatter_unpack": [P, P, L, P, P],
     "hd_gn_stats": [I, P, I, P, I, I, L, I, P, P],
     "hd_gn_apply": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P],
-    "hd_gn_bwd_reduce": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P],
-    "hd_gn_bwd_apply": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P, P, P, P, P, L, I, P],
+    "hd_gn_bwd_reduce": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P, P],
+    "hd_gn_bwd_apply": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P, P, P, P, P, L, I, I, P],
     "hd_gn_bwd_fused": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P, P, P, P, P, P, P],
     "hd_colsum": [I, P, I, I, L, I, P, L, P, P],
     "hd_q_sample": [P, P, P, P, P, P, I, L, P],

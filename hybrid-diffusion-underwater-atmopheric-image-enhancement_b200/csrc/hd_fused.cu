@@ -249,7 +249,7 @@ extern "C" int hd_gn_apply(int dtype, const void* in0, int C0, const void* in1, 
 template <typename T>
 __device__ __forceinline__ void gn_bwd_reduce_body(const Src2<T>& x, const GnParams& g, const T* dy, int64_t pix_per_block,
                                                    double* gsums, float* dgamma, float* dbeta, int n, int blk,
-                                                   float* s_mean, float* s_rstd, float (*sg)[2], float* s_ch) {
+                                                   float* s_mean, float* s_rstd, float (*sg)[2], float* s_ch, T* dy_act = nullptr) {
     constexpr int V = Vec<T>::N;
     gn_load_stats(g, n, s_mean, s_rstd);
     for (int i = threadIdx.x; i < g.G; i += blockDim.x) { sg[i][0] = 0.f; sg[i][1] = 0.f; }
@@ -296,7 +296,11 @@ __device__ __forceinline__ void gn_bwd_reduce_body(const Src2<T>& x, const GnPar
                 if (drop) dd *= ds[k];
                 if (g.act) dd *= hd_swish_grad_t<Vec<T>::fast>(fmaf(v[k], A1[k], B1[k]));
                 s1[k] += dd; s2[k] = fmaf(dd, v[k], s2[k]);
+                d[k] = dd;
             }
+            // dy' = dy * dropout mask * act'(z) handed to the apply pass (usually in place over dy), which then needs neither
+            // the sigmoid nor the dropout hash: both passes are bound by their instruction count, not by HBM
+            if (dy_act) vec_store(dy_act + obase, d);
           }
         }
 #pragma unroll
@@ -318,29 +322,30 @@ __device__ __forceinline__ void gn_bwd_reduce_body(const Src2<T>& x, const GnPar
 }
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> x, GnParams g, const T* dy, int64_t pix_per_block,
-                                                            double* gsums, float* dgamma, float* dbeta) {
+                                                            double* gsums, float* dgamma, float* dbeta, T* dy_act) {
     __shared__ float s_mean[64], s_rstd[64], sg[64][2];
     extern __shared__ float s_ch[];               // [2][C]: per-channel (dgamma, dbeta) partials of this block
-    gn_bwd_reduce_body<T>(x, g, dy, pix_per_block, gsums, dgamma, dbeta, blockIdx.y, blockIdx.x, s_mean, s_rstd, sg, s_ch);
+    gn_bwd_reduce_body<T>(x, g, dy, pix_per_block, gsums, dgamma, dbeta, blockIdx.y, blockIdx.x, s_mean, s_rstd, sg, s_ch, dy_act);
 }
 template <typename T>
 static int gn_bwd_reduce_t(const void* in0, int C0, const void* in1, int C1, GnParams g, const void* dy, double* gsums,
-                           float* dgamma, float* dbeta, cudaStream_t st) {
+                           float* dgamma, float* dbeta, void* dy_act, cudaStream_t st) {
     int rc = gn_check<T>(C0, C1, g.G); if (rc) return rc;
     if (cudaMemsetAsync(gsums, 0, sizeof(double) * 2 * (size_t)g.N * g.G, st) != cudaSuccess) return HD_ERR_CUDA;
     int ppi = 256 / (g.C / Vec<T>::N), chunks;
     int64_t ppb = pick_chunk(g.N, g.HW, ppi, &chunks);
-    gn_bwd_reduce_kernel<T><<<dim3(chunks, g.N), 256, 2 * g.C * sizeof(float), st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (const T*)dy, ppb, gsums, dgamma, dbeta);
+    gn_bwd_reduce_kernel<T><<<dim3(chunks, g.N), 256, 2 * g.C * sizeof(float), st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (const T*)dy, ppb, gsums, dgamma, dbeta, (T*)dy_act);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }
 extern "C" int hd_gn_bwd_reduce(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G,
                                 const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
-                                uint64_t seed, const void* dy, double* gsums, float* dgamma, float* dbeta, cudaStream_t stream) {
+                                uint64_t seed, const void* dy, double* gsums, float* dgamma, float* dbeta, void* dy_act,
+                                cudaStream_t stream) {
     HD_REQUIRE(in0 && sums && gamma && beta && dy && gsums && dgamma && dbeta && (C1 == 0 || in1));
     GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
-    if (dtype == HD_F32) return gn_bwd_reduce_t<float>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, stream);
-    if (dtype == HD_BF16) return gn_bwd_reduce_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, stream);
+    if (dtype == HD_F32) return gn_bwd_reduce_t<float>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, dy_act, stream);
+    if (dtype == HD_BF16) return gn_bwd_reduce_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, dy_act, stream);
     return HD_ERR_ARG;
 }
 
@@ -351,7 +356,8 @@ template <typename T>
 __device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& x, const GnParams& g, const T* dy, const double* gsums, const T* add,
                                                   const T* acc0, const T* acc1, T* dx0, T* dx1, int64_t pix_per_block, int n, int blk,
                                                   float* s_mean, float* s_rstd, float* s_a, float* s_b,
-                                                  float* cs_total, float* cs_per_n, int64_t cs_ld, int cs_n, float* s_cs) {
+                                                  float* cs_total, float* cs_per_n, int64_t cs_ld, int cs_n, float* s_cs,
+                                                  bool dy_is_act = false) {
     constexpr int V = Vec<T>::N;
     const bool want_cs = cs_total || cs_per_n;     // column sums of dx: the bias / embedding-add gradients of the producing conv
     if (want_cs) for (int i = threadIdx.x; i < g.C; i += blockDim.x) s_cs[i] = 0.f;
@@ -384,7 +390,8 @@ __device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& x, const GnPara
     T* dx = first ? dx0 : dx1;
     const int64_t p0 = blk * pix_per_block;
     const int64_t p1 = p0 + pix_per_block < g.HW ? p0 + pix_per_block : g.HW;
-    const bool drop = g.p_drop > 0.f;
+    const bool drop = g.p_drop > 0.f && !dy_is_act;            // dy_is_act: dy already carries the dropout mask and act'(z)
+    const bool act = g.act && !dy_is_act;
     float cs[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) cs[k] = 0.f;
@@ -409,7 +416,7 @@ __device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& x, const GnPara
         for (int k = 0; k < V; ++k) {
             float dd = d[k];
             if (drop) dd *= ds[k];
-            if (g.act) dd *= hd_swish_grad_t<Vec<T>::fast>(fmaf(v[k], A1[k], B1[k]));
+            if (act) dd *= hd_swish_grad_t<Vec<T>::fast>(fmaf(v[k], A1[k], B1[k]));
             r[k] = fmaf(A1[k], dd, -fmaf(v[k], D1[k], C1[k]));
         }
         if (add) { float t[V]; unpack(ar, t);
@@ -454,11 +461,11 @@ __device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& x, const GnPara
 template <typename T>
 __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(Src2<T> x, GnParams g, const T* dy, const double* gsums, const T* add,
                                                            const T* acc0, const T* acc1, T* dx0, T* dx1, int64_t pix_per_block,
-                                                           float* cs_total, float* cs_per_n, int64_t cs_ld, int cs_n) {
+                                                           float* cs_total, float* cs_per_n, int64_t cs_ld, int cs_n, int dy_is_act) {
     __shared__ float s_mean[64], s_rstd[64], s_a[64], s_b[64];
     extern __shared__ float s_cs[];               // [C] column sums of dx of this block
     gn_bwd_apply_body<T>(x, g, dy, gsums, add, acc0, acc1, dx0, dx1, pix_per_block, blockIdx.y, blockIdx.x, s_mean, s_rstd, s_a, s_b,
-                         cs_total, cs_per_n, cs_ld, cs_n, s_cs);
+                         cs_total, cs_per_n, cs_ld, cs_n, s_cs, dy_is_act != 0);
 }
 
 // ------------------------------- backward, both passes in one launch ------------------------
@@ -535,13 +542,13 @@ extern "C" int hd_gn_bwd_fused(int dtype, const void* in0, int C0, const void* i
 template <typename T>
 static int gn_bwd_apply_t(const void* in0, int C0, const void* in1, int C1, GnParams g, const void* dy, const double* gsums,
                           const void* add, const void* acc0, const void* acc1, void* dx0, void* dx1, float* cs_total, float* cs_per_n,
-                          int64_t cs_ld, int cs_n, cudaStream_t st) {
+                          int64_t cs_ld, int cs_n, int dy_is_act, cudaStream_t st) {
     int rc = gn_check<T>(C0, C1, g.G); if (rc) return rc;
     int ppi = 256 / (g.C / Vec<T>::N), chunks;
     int64_t ppb = pick_chunk(g.N, g.HW, ppi, &chunks);
     gn_bwd_apply_kernel<T><<<dim3((unsigned)chunks, g.N), 256, g.C * sizeof(float), st>>>(Src2<T>{(const T*)in0, (const T*)in1, C0, C1}, g, (const T*)dy, gsums,
                                                                   (const T*)add, (const T*)acc0, (const T*)acc1, (T*)dx0, (T*)dx1, ppb,
-                                                                  cs_total, cs_per_n, cs_ld, cs_n);
+                                                                  cs_total, cs_per_n, cs_ld, cs_n, dy_is_act);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }
@@ -549,12 +556,12 @@ extern "C" int hd_gn_bwd_apply(int dtype, const void* in0, int C0, const void* i
                                const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
                                uint64_t seed, const void* dy, const double* gsums, const void* add, const void* acc0,
                                const void* acc1, void* dx0, void* dx1, float* cs_total, float* cs_per_n, int64_t cs_ld,
-                               int cs_n, cudaStream_t stream) {
+                               int cs_n, int dy_is_act, cudaStream_t stream) {
     HD_REQUIRE(in0 && sums && gamma && beta && dy && gsums && dx0 && (C1 == 0 || (in1 && dx1)));
     HD_REQUIRE(cs_n >= 0 && cs_n <= C0 + C1);
     GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
-    if (dtype == HD_F32) return gn_bwd_apply_t<float>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, cs_total, cs_per_n, cs_ld, cs_n, stream);
-    if (dtype == HD_BF16) return gn_bwd_apply_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, cs_total, cs_per_n, cs_ld, cs_n, stream);
+    if (dtype == HD_F32) return gn_bwd_apply_t<float>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, cs_total, cs_per_n, cs_ld, cs_n, dy_is_act, stream);
+    if (dtype == HD_BF16) return gn_bwd_apply_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, cs_total, cs_per_n, cs_ld, cs_n, dy_is_act, stream);
     return HD_ERR_ARG;
 }
 

@@ -543,9 +543,11 @@ class UNetBase(nn.Module):
         gs = torch.empty((N, GN_GROUPS, 2), dtype=torch.float64, device=x0.device)
         dx0 = torch.empty_like(x0)
         dx1 = None if x1 is None else torch.empty_like(x1)
+        # dy is this function's to consume (every caller passes a gradient nobody else reads), unless it doubles as an addend
+        own = dy is not add and dy is not acc0 and dy is not acc1
         ops.gn_bwd(x0, x1, N, H * W, GN_GROUPS, sums, gn.weight, gn.bias, GN_EPS, act, p_drop, seed, dy, gs,
                    st.grad_view(gn.weight), st.grad_view(gn.bias), add, acc0, acc1, dx0, dx1, cs_total=cs_total, cs_per_n=cs_per_n,
-                   cs_n=cs_n)
+                   cs_n=cs_n, overwrite_dy=own)
         return dx0, dx1
 
     def _res_fwd(self, st, rb: ResBlock, idx, x0, x1, emb_all, save, training):

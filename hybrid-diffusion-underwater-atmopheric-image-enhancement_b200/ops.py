@@ -35,6 +35,7 @@ class CudaOps:
         self.use_tc = True          # tcgen05 kernels where the shape is covered
         self.launches = 0           # kernels launched through this object (bench.py reports it)
         self.tc_launches = 0
+        self.gn_inplace = __import__("os").environ.get("HDIFF_GN_INPLACE", "1") != "0"   # GroupNorm backward: the reduce pass hands dy' to the apply pass in place
         self.gn_fused = __import__("os").environ.get("HDIFF_GN_FUSED", "0") != "0"   # one cooperative launch per GroupNorm backward (measured slower: see DESIGN.md)
         self._gn_counter = None
         self.prof = None            # bench.py: dict family -> [(start_event, end_event, work)], CUDA events on the launch stream
@@ -168,9 +169,11 @@ class CudaOps:
         self._t1(e0, "gn_apply", float(2 * N * HW * (C0 + C1) * x0.element_size()))
 
     def gn_bwd(self, x0, x1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, dy, gsums, dgamma, dbeta,
-               add, acc0, acc1, dx0, dx1, cs_total=None, cs_per_n=None, cs_n=None):
+               add, acc0, acc1, dx0, dx1, cs_total=None, cs_per_n=None, cs_n=None, overwrite_dy=False):
         """dgamma/dbeta accumulate; dx0/dx1 are overwritten with dx (+ add + acc0/acc1).  cs_total[c] / cs_per_n[n, c]
-        (optional, accumulate) receive the column sums of dx for the leading cs_n channels (default: all)."""
+        (optional, accumulate) receive the column sums of dx for the leading cs_n channels (default: all).
+        overwrite_dy: the caller does not need dy afterwards — the reduce pass leaves dy * mask * act'(z) in it and the apply
+        pass reads that instead of recomputing the sigmoid and the dropout hash."""
         C0, C1 = x0.shape[-1], 0 if x1 is None else x1.shape[-1]
         dt = _DT[x0.dtype]
         e0 = self._t0()
@@ -182,10 +185,12 @@ class CudaOps:
                                                 _p(self._gn_counter), _stream()), "hd_gn_bwd_fused")
             self.launches += 1
         else:
-            _lib.check(self.lib.hd_gn_bwd_reduce(*a, _p(gsums), _p(dgamma), _p(dbeta), _stream()), "hd_gn_bwd_reduce")
+            inplace = bool(overwrite_dy) and self.gn_inplace and (act or p_drop > 0)
+            _lib.check(self.lib.hd_gn_bwd_reduce(*a, _p(gsums), _p(dgamma), _p(dbeta), _p(dy) if inplace else None, _stream()),
+                       "hd_gn_bwd_reduce")
             _lib.check(self.lib.hd_gn_bwd_apply(*a, _p(gsums), _p(add), _p(acc0), _p(acc1), _p(dx0), _p(dx1), _p(cs_total), _p(cs_per_n),
                                                 0 if cs_per_n is None else cs_per_n.stride(0),
-                                                (C0 + C1) if cs_n is None else int(cs_n), _stream()), "hd_gn_bwd_apply")
+                                                (C0 + C1) if cs_n is None else int(cs_n), int(inplace), _stream()), "hd_gn_bwd_apply")
             self.launches += 2
         nt = 5 + (add is not None) + (acc0 is not None)       # x, dy twice; dx once; optional addends
         self._t1(e0, "gn_bwd", float(nt * N * HW * (C0 + C1) * x0.element_size()))

@@ -88,12 +88,15 @@ int hd_gn_apply(int dtype, const void* in0, int C0, const void* in1, int C1, int
                 hd_stream_t stream);
 int hd_gn_bwd_reduce(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G,
                      const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
-                     uint64_t seed, const void* dy, double* gsums, float* dgamma, float* dbeta, hd_stream_t stream);
+                     uint64_t seed, const void* dy, double* gsums, float* dgamma, float* dbeta, void* dy_act,
+                     hd_stream_t stream);
+/* dy_act (optional, may alias dy): receives dy' = dy * dropout mask * act'(z); hd_gn_bwd_apply(dy = dy_act, dy_is_act = 1) then
+ * skips the sigmoid and the dropout hash */
 int hd_gn_bwd_apply(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G,
                     const double* sums, const float* gamma, const float* beta, float eps, int act, float p_drop,
                     uint64_t seed, const void* dy, const double* gsums, const void* add, const void* acc0,
                     const void* acc1, void* dx0, void* dx1, float* cs_total, float* cs_per_n, int64_t cs_ld,
-                    int cs_n, hd_stream_t stream);
+                    int cs_n, int dy_is_act, hd_stream_t stream);
 /* for c < cs_n: cs_total[c] += sum_{n,pix} dx, cs_per_n[n*cs_ld + c] += sum_pix dx (either may be NULL): the bias and embedding-add
  * gradients of the convolution that produced the normalised tensor, without another pass over dx */
 /* both passes in one cooperative launch, the batch walked in L2-sized image groups (3 HBM tensor passes instead of 5);

@@ -133,7 +133,7 @@ class EmuOps:
         self.launches += 1
 
     def gn_bwd(self, x0, x1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, dy, gsums, dgamma, dbeta,
-               add, acc0, acc1, dx0, dx1, cs_total=None, cs_per_n=None, cs_n=None):
+               add, acc0, acc1, dx0, dx1, cs_total=None, cs_per_n=None, cs_n=None, overwrite_dy=False):
         assert p_drop == 0
         x = self._cat(x0, x1).reshape(N, HW, -1).clone().requires_grad_(True)
         gam = gamma.detach().float().clone().requires_grad_(True)

@@ -367,6 +367,36 @@ def test_conv_alternate_kernel_modes(env):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_groupnorm_backward_in_place_dy():
+    """ops.gn_bwd(overwrite_dy=True): the reduce pass leaves dy * mask * act'(z) in dy and the apply pass consumes it; same
+    results as the two independent passes up to the bf16 rounding of that intermediate."""
+    dev = torch.device("cuda")
+    ops = _ops()
+    torch.manual_seed(9)
+    N, HW, C = 3, 24 * 24, 128
+    x = (torch.randn(N, HW, 1, C, device=dev) * 1.5 + 0.3).to(torch.bfloat16)
+    dy = torch.randn(N, HW, 1, C, device=dev).to(torch.bfloat16)
+    add = torch.randn(N, HW, 1, C, device=dev).to(torch.bfloat16)
+    gamma, beta = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    sums = torch.empty(N, 32, 2, dtype=torch.float64, device=dev)
+    ops.gn_stats(x, None, N, HW, 32, sums)
+    res = []
+    for inplace in (False, True):
+        d = dy.clone()
+        gs = torch.empty(N, 32, 2, dtype=torch.float64, device=dev)
+        dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        dx = torch.empty_like(x)
+        cs = torch.zeros(C, device=dev)
+        ops.gn_bwd(x, None, N, HW, 32, sums, gamma, beta, 1e-5, 1, 0.1, 77, d, gs, dg, db, add, None, None, dx, None, cs_total=cs,
+                   overwrite_dy=inplace)
+        res.append((dx.float(), dg, db, gs, cs, d))
+    assert not torch.equal(res[1][5], dy) and torch.equal(res[0][5], dy)      # the second call did overwrite its dy
+    assert _rel(res[1][0], res[0][0]) < 4e-3
+    for i in (1, 2, 3):
+        assert torch.allclose(res[1][i].double(), res[0][i].double(), rtol=1e-4, atol=1e-4)       # the sums do not see the rounding (fp32 atomics: order)
+    assert _rel(res[1][4], res[0][4]) < 2e-3
+
+
 def test_embedding_path_and_packing_kernels():
     dev = torch.device("cuda")
     ops, emu = _ops(), EmuOps()
