@@ -188,3 +188,30 @@ def test_ddim_sampler_vs_reference_golden(golden_dir):
     assert stride == 50 and coef.shape == (20, 3) and float(coef[:, 2].abs().max()) == 0.0
     ab = sa.alphas_bar
     assert abs(float(coef[0, 0]) - float((ab[0].float().sqrt() / ab[1].float().sqrt()))) < 1e-7
+
+
+def test_ddim_unconditional_and_default_steps_vs_oracle():
+    """DDIM without labels (no guidance pair) and with a real (tiny) UNet on the operator test double, against the oracle."""
+    cfg = dict(T=40, ch=32, ch_mult=[1, 1], attn=[1], num_res_blocks=1, dropout=0.0)
+    torch.manual_seed(5)
+    ref = R.UNet(**cfg).eval()
+    net = UNetU(compute_dtype=torch.float32, **cfg)
+    net.load_state_dict(ref.state_dict())
+    net.eval()
+    xT = torch.randn(2, 3, 8, 8)
+    sa = GaussianDiffusionSampler(net, 1e-4, 0.02, cfg["T"])
+    y0 = sa(xT, ddim=True, ddim_step=8)
+    with torch.no_grad():
+        r0 = R.ddim_sample(ref, 1e-4, 0.02, cfg["T"], xT, None, 1., 8)
+    assert torch.allclose(y0, r0, atol=2e-4), float((y0 - r0).abs().max())
+    # conditional, guided
+    torch.manual_seed(6)
+    refc = R.UNet(num_labels=4, **cfg).eval()
+    netc = UNetC(num_labels=4, compute_dtype=torch.float32, **cfg)
+    netc.load_state_dict(refc.state_dict())
+    netc.eval()
+    lab = torch.tensor([2, 4])
+    y0 = GaussianDiffusionSampler(netc, 1e-4, 0.02, cfg["T"], w=1.5)(xT, lab, ddim=True, ddim_step=10)
+    with torch.no_grad():
+        r0 = R.ddim_sample(refc, 1e-4, 0.02, cfg["T"], xT, lab, 2.5, 10)
+    assert torch.allclose(y0, r0, atol=2e-4), float((y0 - r0).abs().max())
