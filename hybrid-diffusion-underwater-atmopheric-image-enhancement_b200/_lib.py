@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhdiff_b200.so")
 
-P, I, L, F, U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
+P, I, L, F, U64, D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_double
 
 # name -> argument types (all return int status).  Kept in the order of include/hdiff_b200.h.
 PROTOTYPES = {
@@ -29,21 +29,17 @@ PROTOTYPES = {
     "hd_gn_bwd_apply": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P, P, P, P, P, L, I, I, P],
     "hd_gn_bwd_fused": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P, P, P, P, P, P, P],
     "hd_colsum": [I, P, I, I, L, I, P, L, P, P],
-    "hd_q_sample": [P, P, P, P, P, P, I, L, P],
+    "hd_q_sample": [P, P, P, P, P, P, I, L, I, P],
     "hd_mse_fwd": [P, P, P, L, P],
     "hd_mse_bwd": [P, P, P, P, L, P],
     "hd_sampler_step": [P, P, P, P, F, F, P, P, I, P, L, P],
     "hd_add_int": [P, I, P],
-    "hd_sqnorm": [P, L, P, P],
-    "hd_adamw_flat": [P, P, P, P, L, P, F, F, F, F, F, F, I, P],
+    "hd_sqnorm": [P, L, P, I, P],
+    "hd_adamw_flat": [P, P, P, P, L, P, F, D, D, D, D, D, I, P],
     "hd_conv_tc": [P, I, P, I, I, P, P, P, L, P, P, I, I, I, I, I, I, I, P, P],
     "hd_gn_group_sums": [P, I, P, I, I, I, P, P],
     "hd_pad_nchw": [P, I, P, I, L, P],
-    "hd_probe_shift": [P, P, P, I, I, P],
-    "hd_conv_dbg_read": [P],
     "hd_conv_tc_stats_staged": [I, I, I, I, I, I, I, I],
-    "hd_probe_queue": [P, P, I, I, I, I, I, P, P],
-    "hd_probe_pair": [P, P, P, I, I, I, I, P, I, I, I, I, I, P],
     "hd_conv_tc_supported": [I, I, I, I, I, I, I, I],
     "hd_wgrad_tc": [P, I, P, I, I, P, I, I, P, P, L, I, I, I, I, P],
     "hd_wgrad_tc_supported": [I, I, I, I, I, I, I, I],
@@ -58,6 +54,15 @@ PROTOTYPES = {
 }
 NON_STATUS = {"hd_conv_tc_supported", "hd_conv_tc_stats_staged", "hd_wgrad_tc_supported", "hd_attn_tc_supported", "hd_attn_bwd_tc_supported", "hd_attn_wide_tc_supported",
               "hd_wgrad_tc_workspace"}
+
+# lab library only (include/hdiff_b200_lab.h): hardware probes and timing experiments, not part of the product ABI
+LAB_PROTOTYPES = {
+    "hd_probe_shift": [P, P, P, I, I, P],
+    "hd_conv_dbg_read": [P],
+    "hd_probe_queue": [P, P, I, I, I, I, I, P, P],
+    "hd_probe_pair": [P, P, P, I, I, I, I, P, I, I, I, I, I, P],
+}
+LAB_LIB_PATH = os.path.join(HERE, "libhdiff_b200_lab.so")
 
 _lib = None
 
@@ -83,6 +88,20 @@ def load():
         fn.argtypes = args
         fn.restype = L if name == "hd_wgrad_tc_workspace" else I
     _lib = lib
+    return lib
+
+
+def load_lab():
+    """The lab build (product kernels compiled with -DHDIFF_LAB + the probes): scripts/probe_*.py and scripts/conv_clock.py only."""
+    if not os.path.exists(LAB_LIB_PATH):
+        raise HdiffError(f"{LAB_LIB_PATH} is missing: run `python -m hdiff_b200.build --lab`")
+    lib = C.CDLL(LAB_LIB_PATH)
+    lib.hd_last_error.restype = C.c_char_p
+    for table in (PROTOTYPES, LAB_PROTOTYPES):
+        for name, args in table.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = L if name == "hd_wgrad_tc_workspace" else I
     return lib
 
 

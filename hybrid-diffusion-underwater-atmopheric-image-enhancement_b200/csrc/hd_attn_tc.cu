@@ -717,18 +717,18 @@ extern "C" int hd_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)C);
     p.out = (__nv_bfloat16*)out; p.lse = lse;
     const size_t smem = kQBytes + kStages * kStageBytes + 1024 + 16 * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (!hd_seen_on_device(&attr_set)) {
         if (cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(attn_fwd_tc_kernel)"); return HD_ERR_CUDA; }
-        attr_set = true;
+        hd_mark_on_device(&attr_set);
     }
     static const bool use_v2 = !(getenv("HDIFF_ATTN_FWD_V1"));
     if (use_v2 && S % (2 * BM) == 0) {
         const size_t smem2 = kF2Stages * kStageBytes + 1024 + 32 * 8;
-        static bool attr2 = false;
-        if (!attr2) {
+        static unsigned long long attr2 = 0;
+        if (!hd_seen_on_device(&attr2)) {
             if (cudaFuncSetAttribute(attn_fwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(attn_fwd2_tc_kernel)"); return HD_ERR_CUDA; }
-            attr2 = true;
+            hd_mark_on_device(&attr2);
         }
         attn_fwd2_tc_kernel<<<dim3(S / (2 * BM), N), kF2Threads, smem2, stream>>>(m, (const __nv_bfloat16*)qkv, p);
         HD_CHECK_LAUNCH();
@@ -758,13 +758,13 @@ extern "C" int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout
     p.stats = (const float2*)stats; p.dqkv = (__nv_bfloat16*)dqkv;
     p.qkv = (const __nv_bfloat16*)qkv; p.dout = (const __nv_bfloat16*)dout;
     const size_t smem = 168 * 1024;    // key-row pass: 2 x 32 KB + 3 stages; dQ pass: 5 stages (operands in TMEM); + barriers, alignment
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (!hd_seen_on_device(&attr_set)) {
         if (cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
             cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             hd_set_error("cudaFuncSetAttribute(attn_bwd_tc_kernel)"); return HD_ERR_CUDA;
         }
-        attr_set = true;
+        hd_mark_on_device(&attr_set);
     }
     attn_bwd_tc_kernel<false><<<dim3(S / BM, N), kBwdThreads, smem, stream>>>(mQKV, mDO, p);
     HD_CHECK_LAUNCH();

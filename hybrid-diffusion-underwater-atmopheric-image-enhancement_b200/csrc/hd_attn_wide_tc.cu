@@ -484,10 +484,10 @@ extern "C" int hd_attn_fwd_wide_tc(const void* qkv, void* out, float* lse, int N
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)C);
     p.out = (__nv_bfloat16*)out; p.lse = lse;
     const size_t smem = kWfStages * kWfSlot + 1024 + 16 * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (!hd_seen_on_device(&attr_set)) {
         if (cudaFuncSetAttribute(attn_fwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(attn_fwd_wide_kernel)"); return HD_ERR_CUDA; }
-        attr_set = true;
+        hd_mark_on_device(&attr_set);
     }
     attn_fwd_wide_kernel<<<dim3(S / BM, N, C / ZC), kWfThreads, smem, stream>>>(m, p);
     HD_CHECK_LAUNCH();
@@ -510,13 +510,13 @@ extern "C" int hd_attn_bwd_wide_tc(const void* qkv, const void* out, const void*
     p.scale_log2 = 1.4426950408889634f * p.scale;
     p.stats = (const float2*)stats; p.dqkv = (__nv_bfloat16*)dqkv;
     const size_t smem = kWbStages * kWbSlot + 8 * 2 * 32 * 8 + 1024 + 24 * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (!hd_seen_on_device(&attr_set)) {
         if (cudaFuncSetAttribute(attn_bwd_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
             cudaFuncSetAttribute(attn_bwd_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             hd_set_error("cudaFuncSetAttribute(attn_bwd_wide_kernel)"); return HD_ERR_CUDA;
         }
-        attr_set = true;
+        hd_mark_on_device(&attr_set);
     }
     const dim3 grid(S / BM, N, C / ZC);
     attn_bwd_wide_kernel<false><<<grid, kWbThreads, smem, stream>>>(mQKV, mDO, p);

@@ -98,6 +98,13 @@ __device__ __forceinline__ float hd_warp_max(float v) {
     return v;
 }
 
+
+// Kernel attributes (opt-in shared memory) are PER DEVICE: `seen` is one flag word per call site, one bit per device ordinal.
+// Usage: if (!hd_seen_on_device(&flags)) { cudaFuncSetAttribute(...); hd_mark_on_device(&flags); }  (setting twice is harmless)
+static inline unsigned long long hd_device_bit() { int dev = 0; cudaGetDevice(&dev); return 1ull << (dev & 63); }
+static inline bool hd_seen_on_device(const unsigned long long* seen) { return (__atomic_load_n(seen, __ATOMIC_ACQUIRE) & hd_device_bit()) != 0; }
+static inline void hd_mark_on_device(unsigned long long* seen) { __atomic_fetch_or(seen, hd_device_bit(), __ATOMIC_ACQ_REL); }
+
 static inline int hd_num_sms() {
     static int n = 0;
     if (n == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }

@@ -36,8 +36,14 @@ constexpr int kThreads = 32 * (3 + kEpiWarps + kProducers - 1);
 constexpr int kABytes = 128 * 128;     // 128 pixels x 64 bf16
 constexpr int kMaxStages = 8;
 
-// HDIFF_CONV_DBG & 4: CTA 0 records (clock64, globaltimer) at its start and end: the SM clock DURING the kernel
+// Timing experiments (HDIFF_CONV_DBG) exist only in the lab build (-DHDIFF_LAB, libhdiff_b200_lab.so): the product library
+// carries neither the switch nor its branches.  & 4: CTA 0 records (clock64, globaltimer) at its start and end.
+#ifdef HDIFF_LAB
 __device__ long long g_conv_dbg[4];
+#define HD_CONV_DBG(p) ((p).dbg)
+#else
+#define HD_CONV_DBG(p) 0
+#endif
 
 struct ConvTcParams {
     int N, H, W, TH, TW, tiles_x, tiles_y, m_tiles, n_tiles, NT;
@@ -88,10 +94,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     float* stat_s = addend + 2 * 256;                                        // [2][256][2]: per-tile channel sums (p.chan_sums)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef HDIFF_LAB
     if ((p.dbg & 4) && blockIdx.x == 0 && threadIdx.x == 0) {
         long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_conv_dbg[0] = clock64(); g_conv_dbg[1] = t;
     }
+#endif
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA0); tma_prefetch_desc(&mapA1); tma_prefetch_desc(&mapB);
         if (p.stage_out) { tma_prefetch_desc(&mapOut); if (kRes) tma_prefetch_desc(&mapRes); }
@@ -146,7 +154,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             for (int cc = 0; cc < p.nchunk_c; ++cc) {
                                 if (turn == prod) {
                                     mbar_wait(&empty[stage], phase ^ 1);
-                                    if (p.dbg & 2) { mbar_arrive(&full[stage]); goto txm_next; }
+                                    if (HD_CONV_DBG(p) & 2) { mbar_arrive(&full[stage]); goto txm_next; }
                                     {
                                     mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_tx);
                                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -357,7 +365,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
-            if (p.dbg & 1) {
+            if (HD_CONV_DBG(p) & 1) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -591,10 +599,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+#ifdef HDIFF_LAB
     if ((p.dbg & 4) && blockIdx.x == 0 && threadIdx.x == 0) {
         long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_conv_dbg[2] = clock64(); g_conv_dbg[3] = t;
     }
+#endif
 }
 
 int pick_nt(int CoutL) {
@@ -645,8 +655,12 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
                     if (stages_of(t, w, g) >= (t ? 3 : 2)) { txm = t; wres = w; stage = g; found = true; }
         if (!found) return false;
         p.txm = txm; p.wres = wres; p.stage_out = stage;
+#ifdef HDIFF_LAB
         static const int dbg = getenv("HDIFF_CONV_DBG") ? atoi(getenv("HDIFF_CONV_DBG")) : 0;
         p.dbg = dbg;
+#else
+        p.dbg = 0;
+#endif
         static const int contig_env = getenv("HDIFF_CONV_CONTIG") ? atoi(getenv("HDIFF_CONV_CONTIG")) : -1;
         p.contig = contig_env >= 0 ? contig_env : (chan_sums && stage ? 1 : 0);
         // second issuer.  Mode 1 (alternate tiles): a gain where the issuing thread is the bottleneck (64->64: 0.201 -> 0.178 ms),
@@ -769,15 +783,15 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
         rc = hd_make_tmap_bf16(&mB, w, 2, dims, str, box); if (rc) return rc;
     }
     const size_t smem = (size_t)p.stages * stage_bytes + (p.stage_out ? 2 * kABytes : 0) + (p.wres ? (size_t)CoutL * p.kb_w * 128 : 0) + 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 2 * 256 * 4 + 2 * 512 * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (!hd_seen_on_device(&attr_set)) {
         if (cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             hd_set_error("cudaFuncSetAttribute(conv_tc_kernel)"); return HD_ERR_CUDA;
         }
-        attr_set = true;
+        hd_mark_on_device(&attr_set);
     }
     int grid = p.m_tiles * p.n_tiles; const int sms = hd_num_sms(); if (grid > sms) grid = sms;
     if (chan_sums && !p.stage_out) {          // (the staged epilogue takes its statistics from the staged tile, no template flag)
@@ -792,11 +806,13 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
 }
 
 // timing experiments: (clock64, globaltimer ns) at the start and the end of CTA 0 of the last hd_conv_tc launch with HDIFF_CONV_DBG & 4
+#ifdef HDIFF_LAB
 extern "C" int hd_conv_dbg_read(long long* out4) {
     HD_REQUIRE(out4);
     if (cudaMemcpyFromSymbol(out4, g_conv_dbg, sizeof(long long) * 4) != cudaSuccess) { hd_set_error("cudaMemcpyFromSymbol"); return HD_ERR_CUDA; }
     return HD_OK;
 }
+#endif
 
 // 1 if a launch of this shape with `chan_sums` takes the staged epilogue, where the GroupNorm statistics of the output are
 // read back out of the staged tile in shared memory (cheap); 0 if it would run the register butterfly of the direct-store

@@ -670,20 +670,22 @@ extern "C" int hd_pad_nchw(const float* in, int Cin, void* out, int N, int64_t H
 // ------------------------------- K6: q_sample / MSE ------------------------------------------
 // x_t = sqrt_ab[t[n]] * x0 + sqrt_1m_ab[t[n]] * noise     (fp32 NCHW, chw elements per sample)
 __global__ void q_sample_kernel(const float4* x0, const float4* noise, const int64_t* t, const float* sab, const float* s1ab,
-                                float4* xt, int64_t chw4) {
+                                float4* xt, int64_t chw4, int T) {
     const int n = blockIdx.y;
-    const float a = sab[t[n]], b = s1ab[t[n]];
+    const int64_t tn = t[n];
+    if (tn < 0 || tn >= T) { if (threadIdx.x == 0 && blockIdx.x == 0) printf("hd_q_sample: t = %lld out of range [0, %d)\n", (long long)tn, T); __trap(); }
+    const float a = sab[tn], b = s1ab[tn];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < chw4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 u = x0[n * chw4 + i], v = noise[n * chw4 + i];
         xt[n * chw4 + i] = make_float4(a * u.x + b * v.x, a * u.y + b * v.y, a * u.z + b * v.z, a * u.w + b * v.w);
     }
 }
 extern "C" int hd_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sab, const float* s1ab, float* xt,
-                           int N, int64_t chw, cudaStream_t stream) {
-    HD_REQUIRE(x0 && noise && t && sab && s1ab && xt && N > 0 && chw > 0 && chw % 4 == 0);
+                           int N, int64_t chw, int T, cudaStream_t stream) {
+    HD_REQUIRE(x0 && noise && t && sab && s1ab && xt && N > 0 && chw > 0 && chw % 4 == 0 && T > 0);
     int64_t chw4 = chw / 4;
     int64_t bx = (chw4 + 255) / 256; if (bx > 1024) bx = 1024;
-    q_sample_kernel<<<dim3((unsigned)bx, N), 256, 0, stream>>>((const float4*)x0, (const float4*)noise, t, sab, s1ab, (float4*)xt, chw4);
+    q_sample_kernel<<<dim3((unsigned)bx, N), 256, 0, stream>>>((const float4*)x0, (const float4*)noise, t, sab, s1ab, (float4*)xt, chw4, T);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }
@@ -769,9 +771,9 @@ __global__ void sqnorm_kernel(const float4* g, int64_t n4, double* out) {
     __syncthreads();
     if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w]; atomicAdd(out, (double)t); }
 }
-extern "C" int hd_sqnorm(const float* g, int64_t n, double* out, cudaStream_t stream) {
+extern "C" int hd_sqnorm(const float* g, int64_t n, double* out, int accumulate, cudaStream_t stream) {
     HD_REQUIRE(g && out && n > 0 && n % 4 == 0);
-    if (cudaMemsetAsync(out, 0, sizeof(double), stream) != cudaSuccess) return HD_ERR_CUDA;
+    if (!accumulate && cudaMemsetAsync(out, 0, sizeof(double), stream) != cudaSuccess) return HD_ERR_CUDA;
     int64_t b = (n / 4 + 255) / 256; if (b > 148 * 8) b = 148 * 8;
     sqnorm_kernel<<<(unsigned)b, 256, 0, stream>>>((const float4*)g, n / 4, out);
     HD_CHECK_LAUNCH();
@@ -781,7 +783,7 @@ extern "C" int hd_sqnorm(const float* g, int64_t n, double* out, cudaStream_t st
 //   clip = min(1, max_norm / (||g|| + 1e-6)); g *= clip
 //   p *= 1 - lr wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void adamw_kernel(float4* p, float4* g, float4* m, float4* v, int64_t n4, const double* sqnorm, float max_norm,
-                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+                             float lr, float b1, float b2, float eps, float decay, float step_size, float bc2_sqrt) {
     float clip = 1.f;
     if (max_norm > 0.f) { float nrm = (float)sqrt(*sqnorm); clip = fminf(1.f, max_norm / (nrm + 1e-6f)); }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -791,21 +793,24 @@ __global__ void adamw_kernel(float4* p, float4* g, float4* m, float4* v, int64_t
         for (int k = 0; k < 4; ++k) {
             float gk = gg[k] * clip;
             gg[k] = gk;
-            pp[k] *= 1.f - lr * wd;
+            pp[k] *= decay;
             mm[k] = b1 * mm[k] + (1.f - b1) * gk;
             vq[k] = b2 * vq[k] + (1.f - b2) * gk * gk;
             float denom = sqrtf(vq[k]) / bc2_sqrt + eps;
-            pp[k] -= (lr / bc1) * (mm[k] / denom);
+            pp[k] -= step_size * (mm[k] / denom);
         }
         p[i] = pv; g[i] = gv; m[i] = mv; v[i] = vv;
     }
 }
-extern "C" int hd_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const double* sqnorm, float max_norm, float lr,
-                             float b1, float b2, float eps, float wd, int step, cudaStream_t stream) {
+extern "C" int hd_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const double* sqnorm, float max_norm, double lr,
+                             double b1, double b2, double eps, double wd, int step, cudaStream_t stream) {
     HD_REQUIRE(p && g && m && v && n > 0 && n % 4 == 0 && step >= 1 && (max_norm <= 0.f || sqnorm));
-    float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+    // bias corrections in double from the caller's double hyper-parameters, as torch.optim.AdamW forms them (in fp32,
+    // 1 - 0.999^step cancels to ~1e-5 relative at small step counts)
+    const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
     int64_t b = (n / 4 + 255) / 256; if (b > 148 * 16) b = 148 * 16;
-    adamw_kernel<<<(unsigned)b, 256, 0, stream>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n / 4, sqnorm, max_norm, lr, b1, b2, eps, wd, bc1, sqrtf(bc2));
+    adamw_kernel<<<(unsigned)b, 256, 0, stream>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n / 4, sqnorm, max_norm, (float)lr, (float)b1, (float)b2,
+                                                  (float)eps, (float)(1.0 - lr * wd), (float)(lr / bc1), (float)sqrt(bc2));
     HD_CHECK_LAUNCH();
     return HD_OK;
 }

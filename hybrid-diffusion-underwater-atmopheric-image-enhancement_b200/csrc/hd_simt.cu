@@ -396,11 +396,15 @@ extern "C" int hd_linear_bwd_w(const float* dy, int M, int Nout, int64_t lddy, c
     return HD_OK;
 }
 
-__global__ void embedding_fwd_kernel(const float* table, int dim, const int64_t* idx, int M, float* out) {
+// An index outside [0, rows) is a caller bug (t >= T, label > num_labels): like torch's device-side assert in nn.Embedding it
+// aborts the launch (sticky error on the context) instead of reading out of bounds.
+__global__ void embedding_fwd_kernel(const float* table, int rows, int dim, const int64_t* idx, int M, float* out) {
     int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (o >= (int64_t)M * dim) return;
     int m = (int)(o / dim), d = (int)(o % dim);
-    out[o] = table[idx[m] * dim + d];
+    const int64_t r = idx[m];
+    if (r < 0 || r >= rows) { if (d == 0) printf("hd_embedding_fwd: index %lld out of range [0, %d)\n", (long long)r, rows); __trap(); }
+    out[o] = table[r * dim + d];
 }
 __global__ void embedding_bwd_kernel(const float* dout, int dim, const int64_t* idx, int M, float* dtable, int64_t padding_idx) {
     int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -413,7 +417,7 @@ __global__ void embedding_bwd_kernel(const float* dout, int dim, const int64_t* 
 extern "C" int hd_embedding_fwd(const float* table, int rows, int dim, const int64_t* idx, int M, float* out, cudaStream_t stream) {
     HD_REQUIRE(table && idx && out && rows > 0 && dim > 0 && M > 0);
     int64_t n = (int64_t)M * dim;
-    embedding_fwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(table, dim, idx, M, out);
+    embedding_fwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(table, rows, dim, idx, M, out);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }

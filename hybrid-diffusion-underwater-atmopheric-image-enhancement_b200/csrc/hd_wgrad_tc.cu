@@ -372,10 +372,10 @@ extern "C" int hd_wgrad_tc(const void* in0, int C0, const void* in1, int C1, int
     rc = hd_make_act_tmap(&mDY, dy, Cdy, P_dy, N, H, W, 64, p.TW, p.TH); if (rc) return rc;
     const int stage_bytes = (p.halo ? p.max_units * kHaloSlot : p.G * 2 * kBlkBytes) + p.nb * kBlkBytes;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * kMaxStages + 2) * 8 + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;
+    if (!hd_seen_on_device(&attr_set)) {
         if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { hd_set_error("cudaFuncSetAttribute(wgrad_tc_kernel)"); return HD_ERR_CUDA; }
-        attr_set = true;
+        hd_mark_on_device(&attr_set);
     }
     wgrad_tc_kernel<<<dim3(p.ngroups, p.splits, p.n_tiles), kThreads, smem, stream>>>(mX0, mX1, mDY, p);
     HD_CHECK_LAUNCH();

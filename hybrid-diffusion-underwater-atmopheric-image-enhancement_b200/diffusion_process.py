@@ -119,13 +119,18 @@ class GaussianDiffusionSampler(nn.Module):
         which is the linear update  y_next = k1 y_t - k2 eps  that hd_sampler_step applies, with
             k1 = sqrt(at_next) / sqrt(at),   k2 = sqrt(at_next) sqrt(1 - at) / sqrt(at) - sqrt(1 - at_next)
         and no noise term.  Returns (table [len(seq)][3] fp32 in seq order, stride); the reference hard-codes 1000 for T."""
+        if ddim_step is None:
+            raise ValueError("ddim=True needs ddim_step (number of DDIM steps, e.g. 100; the reference divides by it, Diffusion.py:246)")
         ddim_step = int(ddim_step)
         if ddim_step not in self._ddim:
+            if ddim_step < 1 or ddim_step > self.T:
+                raise ValueError(f"ddim_step must be in [1, T={self.T}]")
             stride = int(self.T / ddim_step)
-            assert stride >= 1 and ddim_step >= 1
             seq = list(range(0, self.T, stride))
             seq_next = [-1] + seq[:-1]
-            assert seq[-1] + 1 < self.T, "alphas_bar is read at t + 1 (Diffusion.py:251)"
+            if seq[-1] + 1 >= self.T:
+                raise ValueError(f"ddim_step={ddim_step} visits t={seq[-1]} and reads alphas_bar[t + 1] (Diffusion.py:251), which is out "
+                                 f"of range for T={self.T}; use a ddim_step whose stride T // ddim_step is >= 2")
             ab = self.alphas_bar
             at = ab[torch.tensor([i + 1 for i in seq], device=ab.device)].float()            # extract(...).float()
             an = ab[torch.tensor([j + 1 for j in seq_next], device=ab.device)].float()
@@ -162,7 +167,10 @@ class GaussianDiffusionSampler(nn.Module):
             eps_u = eps_u.contiguous()
         eps_c = eps_c.contiguous()
         assert eps_c.shape == x.shape
-        z = torch.randn_like(x)                  # ignored by the kernel at t == 0 (the reference adds no noise there)
+        # ancestral: ignored by the kernel at t == 0 (the reference adds no noise there).  DDIM: the reference draws
+        # `c1 * randn_like` with c1 = 0 every step (Diffusion.py:264-265) — the draw is kept so that the generator advances as
+        # the reference's does, the coefficient table's noise column is zero.
+        z = torch.randn_like(x)
         ops.sampler_step(x, eps_c, eps_u, z, self.w, self._coef if coef is None else coef, step, True, nan_flag)
         ops.add_int(step, -1)
 
@@ -198,7 +206,7 @@ class GaussianDiffusionSampler(nn.Module):
         x = x_T.clone().contiguous()
         nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         if ddim:
-            coef, stride = self.ddim_tables(self.T if ddim_step is None else ddim_step)
+            coef, stride = self.ddim_tables(ddim_step)
             coef = coef.to(dev)
             n = coef.shape[0]
             step = torch.full((1,), n - 1, dtype=torch.int32, device=dev)

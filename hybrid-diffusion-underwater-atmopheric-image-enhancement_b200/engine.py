@@ -228,6 +228,16 @@ class UNetBase(nn.Module):
         self.dp_group = None     # set by hdiff_b200.parallel.enable_data_parallel
         self.dp_bucket_bytes = 8 << 20
 
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """As nn.Module.load_state_dict.  A checkpoint of the reference's LIVE ModelCondition.UNet carries
+        nn.MultiheadAttention keys (`attn.in_proj_weight`, `attn.out_proj.*`, ModelCondition.py:189); this class is the
+        AttnBlock variant (`attn.proj_q/k/v`), so under strict=False (TrainCondition.py:36-38) every attention weight would be
+        dropped silently: refuse instead and point at the MHA model."""
+        if not getattr(self, "mha", False) and any(".attn.in_proj_weight" in k or ".attn.out_proj." in k for k in state_dict):
+            raise RuntimeError("this state_dict holds nn.MultiheadAttention weights (the reference's live MHA ResBlock, "
+                               "ModelCondition.py:166-211); build the model with mha=True (hdiff_b200 ... UNet(..., mha=True)) to load it")
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
     # -----------------------------------------------------------------------------------------
     # flat buffers + packed layouts
     # -----------------------------------------------------------------------------------------
@@ -796,6 +806,11 @@ class UNetBase(nn.Module):
         assert not dskip, "unconsumed skip gradients"
         # ---- head ----
         self._wgrad(st, st.head, ctx["x"], None, d_h, in_nchw=not st.pad_io)
+        # ---- data parallel: every packed weight and bias gradient is final here; their exchange runs under the embedding-path
+        #      kernels below (only the small directly-written prefix of the flat buffer has to wait for those) ----
+        if reducer is not None:
+            self._join_side(st)
+            reducer.flush(st.gpk[st.n_dw:])
         # ---- embedding path ----
         fg = st.flat_grad
         te = self.time_embedding.timembedding
@@ -826,11 +841,11 @@ class UNetBase(nn.Module):
             d_c0 = torch.empty_like(c0)
             ops.linear_bwd_x(d_c1, ce[1].weight, None, d_c0)
             ops.embedding_bwd(d_c0, ctx["labels"], gv(ce[0].weight), padding_idx=0)
-        # ---- data parallel: the rest of the packed weight gradients (head / tail / first blocks), the packed bias
-        #      gradients and the directly written part of the flat buffer; then the compute stream waits ----
+        # ---- data parallel: the directly written part of the flat buffer (GroupNorm, Linear, embedding tables); then the
+        #      compute stream waits for every exchange of this step ----
         self._join_side(st)
         if reducer is not None:
-            reducer.finish(st.gpk[st.n_dw:], fg[:st.n_direct])
+            reducer.finish(fg[:st.n_direct])
         # ---- packed conv gradients -> parameter layouts ----
         ops.scatter_unpack(st.gpk, st.inv, fg)
         used_cond = "labels" in ctx
@@ -860,11 +875,16 @@ class _State:
 
 
 class _UNetFunction(torch.autograd.Function):
+    """ONE autograd node for the whole network.  Its tensor inputs are exactly the parameters this forward uses: the
+    unconditional model's `cond_proj.*` (registered for checkpoint compatibility, never used: ModelCondition.py:199-200)
+    are not inputs, so autograd — and torch's DistributedDataParallel, which walks the graph to find the parameters that
+    will receive a gradient — sees them as unused, as it does in the reference."""
+
     @staticmethod
     def forward(fctx, net, x, t, labels, *params):
         with torch.no_grad():
             eps, ctx = net._run_forward(x.detach(), t, labels, save=True)
-        fctx.net, fctx.hd_ctx, fctx.n_params = net, ctx, len(params)
+        fctx.net, fctx.hd_ctx, fctx.param_ids = net, ctx, [id(p) for p in params]
         return eps
 
     @staticmethod
@@ -876,22 +896,17 @@ class _UNetFunction(torch.autograd.Function):
         with torch.no_grad():
             grads, used_cond = net._run_backward(ctx, d_eps)
         st = net._state
-        out = []
-        unused = set()
-        if not used_cond:
-            # cond_proj is registered but never used by the unconditional model (ModelCondition.py:199-200):
-            # no gradient, exactly as in the reference.
-            for rb in net._resblocks():
-                unused.add(id(rb.cond_proj[1].weight))
-                unused.add(id(rb.cond_proj[1].bias))
-        for p, g in zip(st.order, grads):
-            out.append(None if id(p) in unused else g)
-        return (None, None, None, None) + tuple(out)
+        by_id = {id(p): g for p, g in zip(st.order, grads)}
+        return (None, None, None, None) + tuple(by_id[i] for i in fctx.param_ids)
 
 
 def _apply(net, x, t, labels):
     st = net._get_state()
-    return _UNetFunction.apply(net, x, t, labels, *st.order)
+    params = st.order
+    if labels is None:
+        skip = {id(q) for rb in net._resblocks() for q in rb.cond_proj.parameters()}
+        params = [p for p in params if id(p) not in skip]
+    return _UNetFunction.apply(net, x, t, labels, *params)
 
 
 # route UNetBase.forward through the single autograd node

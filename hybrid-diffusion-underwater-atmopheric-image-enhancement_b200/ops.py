@@ -82,6 +82,8 @@ class CudaOps:
             self.tc_launches += 1
             self._t1(e0, "conv_tc", flops)
             return True if chan_sums is not None else None      # True: the per-channel statistics were produced
+        if self.use_tc and dt == BF16:
+            _warn_cuda_core("conv", f"C={C0}+{C1} P_in={P_in} Cout={Cout} P_out={P_out} H={H} W={W} k={k}")
         rc = lib.hd_conv_simt(dt, _p(x0), C0, _p(x1), C1, P_in, int(in_nchw), _p(w), _p(bias), _p(emb),
                               0 if emb is None else emb.stride(0), _p(res), _p(out), Cout, P_out, nchw_c,
                               N, H, W, k, _stream())
@@ -110,6 +112,8 @@ class CudaOps:
             self.tc_launches += 1
             self._t1(e0, "wgrad_tc", flops)
             return
+        if self.use_tc and dt == BF16:
+            _warn_cuda_core("wgrad", f"C={C0}+{C1} P_in={P_in} Cdy={Cdy} P_dy={P_dy} H={H} W={W} k={k}")
         rc = lib.hd_wgrad_simt(dt, _p(x0), C0, _p(x1), C1, P_in, int(in_nchw), _p(dy), Cdy, P_dy, int(dy_nchw),
                                _p(dw), N, H, W, k, _stream())
         _lib.check(rc, "hd_wgrad_simt")
@@ -130,6 +134,8 @@ class CudaOps:
             _lib.check(self.lib.hd_attn_fwd_tc(_p(qkv), _p(out), _p(lse), N, S, C, _stream()), "hd_attn_fwd_tc")
             self.tc_launches += 1
         else:
+            if self.use_tc and qkv.dtype == torch.bfloat16:
+                _warn_cuda_core("attention", f"S={S} C={C}")
             _lib.check(self.lib.hd_attn_fwd_simt(_DT[qkv.dtype], _p(qkv), _p(out), _p(lse), N, S, C, _stream()), "hd_attn_fwd_simt")
         self.launches += 1
         self._t1(e0, "attn_fwd_tc" if tc else "attn_fwd_simt", 4.0 * N * S * S * C)
@@ -243,7 +249,7 @@ class CudaOps:
     # ---- diffusion process ---------------------------------------------------------------
     def q_sample(self, x0, noise, t, sab, s1ab, xt):
         N = x0.shape[0]
-        _lib.check(self.lib.hd_q_sample(_p(x0), _p(noise), _p(t), _p(sab), _p(s1ab), _p(xt), N, x0.numel() // N, _stream()), "hd_q_sample")
+        _lib.check(self.lib.hd_q_sample(_p(x0), _p(noise), _p(t), _p(sab), _p(s1ab), _p(xt), N, x0.numel() // N, sab.numel(), _stream()), "hd_q_sample")
         self.launches += 1
 
     def mse_fwd(self, pred, noise, loss):
@@ -264,14 +270,30 @@ class CudaOps:
         self.launches += 1
 
     # ---- optimizer -----------------------------------------------------------------------
-    def sqnorm(self, g, out):
-        _lib.check(self.lib.hd_sqnorm(_p(g), g.numel(), _p(out), _stream()), "hd_sqnorm")
+    def sqnorm(self, g, out, accumulate=False):
+        """out[0] (fp64) = sum g^2 (accumulate: += , for a norm over several ranges of the flat buffer)"""
+        _lib.check(self.lib.hd_sqnorm(_p(g), g.numel(), _p(out), int(accumulate), _stream()), "hd_sqnorm")
         self.launches += 1
 
     def adamw_flat(self, p, g, m, v, sqnorm, max_norm, lr, b1, b2, eps, wd, step):
         _lib.check(self.lib.hd_adamw_flat(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(sqnorm), float(max_norm), float(lr),
                                           float(b1), float(b2), float(eps), float(wd), int(step), _stream()), "hd_adamw_flat")
         self.launches += 1
+
+
+_warned = set()
+
+
+def _warn_cuda_core(what, detail):
+    """A bf16 shape outside the tcgen05 tiles runs on the CUDA-core kernels (the fp32 check-mode path): correct, but one to
+    two orders of magnitude slower.  Say so once per (operator, shape)."""
+    key = (what, detail)
+    if key in _warned:
+        return
+    _warned.add(key)
+    import warnings
+    warnings.warn(f"hdiff_b200: {what} {detail} is outside the tcgen05 kernels' tiles and runs on the CUDA-core kernel "
+                  f"(much slower); see DESIGN.md for the covered shapes", RuntimeWarning, stacklevel=3)
 
 
 _backend = None

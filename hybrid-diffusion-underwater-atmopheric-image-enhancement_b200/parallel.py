@@ -53,14 +53,19 @@ class GradReducer:
         self.hi = 0
         self.launched = 0                      # number of collectives issued (tests / bench read it)
         self.before_reduce = None              # optional callable run before a collective is enqueued (stream joins)
+        # NCCL averages inside the collective (ReduceOp.AVG); gloo (CPU tests) has no AVG: pre-scale there
+        self.avg = dist.get_backend(group) == "nccl"
 
     def reduce_async(self, chunk: torch.Tensor):
         if self.world == 1 or chunk.numel() == 0:
             return
         if self.before_reduce is not None:
             self.before_reduce()
-        chunk.mul_(1.0 / self.world)
-        self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if self.avg:
+            self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        else:
+            chunk.mul_(1.0 / self.world)
+            self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.launched += 1
 
     def attach(self, buf: torch.Tensor, hi: int):
@@ -72,7 +77,8 @@ class GradReducer:
             self.reduce_async(self.buf[lo:self.hi])
             self.hi = lo
 
-    def finish(self, *extra: torch.Tensor):
+    def flush(self, *extra: torch.Tensor):
+        """Exchange what is left of the walked region plus `extra`, without waiting (more kernels follow)."""
         if self.buf is not None and self.hi > 0:
             self.reduce_async(self.buf[:self.hi])
             self.hi = 0
@@ -80,6 +86,9 @@ class GradReducer:
             n = t.numel()
             for lo in range(0, n, self.bucket):
                 self.reduce_async(t[lo:lo + self.bucket])
+
+    def finish(self, *extra: torch.Tensor):
+        self.flush(*extra)
         self.wait()
 
     def wait(self):

@@ -129,7 +129,7 @@ int hd_scatter_unpack(const float* packed, const int32_t* inv, int64_t n, float*
 /* ---- diffusion process: extract / q_sample / mse_loss (DiffusionCondition.py:9-16,41-45) and one sampler step
  *      p_mean_variance + CFG mix + noise + NaN check + final clip (DiffusionCondition.py:68-98) ---- */
 int hd_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ab, const float* sqrt_1m_ab,
-                float* xt, int N, int64_t chw, hd_stream_t stream);
+                float* xt, int N, int64_t chw, int T, hd_stream_t stream);   /* t outside [0, T) aborts the launch */
 int hd_mse_fwd(const float* pred, const float* noise, float* loss, int64_t n, hd_stream_t stream);
 int hd_mse_bwd(const float* pred, const float* noise, const float* g, float* dpred, int64_t n, hd_stream_t stream);
 int hd_sampler_step(float* x, const float* eps_c, const float* eps_u, const float* z, float w1, float w, const float* coef,
@@ -139,23 +139,10 @@ int hd_add_int(int* p, int delta, hd_stream_t stream);
 /* 1 if hd_conv_tc with `chan_sums` would take the staged epilogue for this shape (statistics read back out of the staged
  * tile: cheap); the host requests conv-epilogue statistics only then */
 int hd_conv_tc_stats_staged(int C0, int C1, int P_in, int Cout, int P_out, int H, int W, int ksize);
-/* timing experiments (HDIFF_CONV_DBG=4): (clock64, globaltimer ns) at the start / end of CTA 0 of the last hd_conv_tc launch */
-int hd_conv_dbg_read(long long* out4);
-/* ---- hardware probe (scripts/probe_shift.py): tcgen05 A operand starting at an arbitrary 128-byte row of a swizzled box ---- */
-int hd_probe_shift(const void* x, const void* w, float* out, int shift, int mode, hd_stream_t stream);
-/* ---- hardware probe (scripts/probe_pair.py): C[256][N] = A[256][K] B[N][K]^T by a CTA pair; mode 1 = each CTA on its own
- *      (tcgen05.mma.cta_group::1), mode 2 = one M = 256 MMA stream for the pair (cta_group::2, each CTA holds half of B);
- *      out accumulates `reps` identical products, cycles[2] = clock64 span of the MMA sequence per CTA ---- */
-int hd_probe_pair(const void* a, const void* b, float* out, int N, int K, int mode, int reps, long long* cycles, int shift,
-                  int fill, int cper, int nclusters, int ring, hd_stream_t stream);
-/* how far the issuing thread can run ahead of the tensor pipe: `groups` x (12 unrolled MMAs + `gap` idle cycles) */
-int hd_probe_queue(const void* a, const void* b, int N, int groups, int gap, int issuers, int second_warp, long long* cycles,
-                   hd_stream_t stream);
-
 /* ---- clip_grad_norm_ + AdamW on the flat buffers (TrainCondition.py:39,61-63) ---- */
-int hd_sqnorm(const float* g, int64_t n, double* out, hd_stream_t stream);
-int hd_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const double* sqnorm, float max_norm, float lr,
-                  float b1, float b2, float eps, float wd, int step, hd_stream_t stream);
+int hd_sqnorm(const float* g, int64_t n, double* out, int accumulate, hd_stream_t stream);   /* accumulate: out += instead of out = */
+int hd_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const double* sqnorm, float max_norm, double lr,
+                  double b1, double b2, double eps, double wd, int step, hd_stream_t stream);   /* bias corrections formed in double */
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,9 @@ os.environ["HDIFF_CONV_DBG"] = os.environ.get("HDIFF_CONV_DBG", "4")
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hdiff_b200.ops as hops
+from hdiff_b200 import _lib
 import pynvml
+_lib._lib = _lib.load_lab()          # the timing modes exist only in the lab build (python -m hdiff_b200.build --lab)
 ops = hops.get()
 dev = torch.device("cuda")
 bf = torch.bfloat16

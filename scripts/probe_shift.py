@@ -3,7 +3,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hdiff_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_lab()          # probes live in the lab library (python -m hdiff_b200.build --lab)
 dev = torch.device("cuda")
 torch.manual_seed(0)
 x = torch.randn(144, 64, device=dev).to(torch.bfloat16)

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    config.addinivalue_line("markers", "slow: minutes-long trajectory parity (200 optimisation steps, 1000 sampler steps)")
 
 
 def pytest_collection_modifyitems(config, items):

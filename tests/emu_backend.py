@@ -263,8 +263,12 @@ class EmuOps:
         self.launches += 1
 
     # ---- optimizer ----
-    def sqnorm(self, g, out):
-        out.copy_((g.double() ** 2).sum().reshape(out.shape))
+    def sqnorm(self, g, out, accumulate=False):
+        v = (g.double() ** 2).sum().reshape(out.shape)
+        if accumulate:
+            out += v
+        else:
+            out.copy_(v)
         self.launches += 1
 
     def adamw_flat(self, p, g, m, v, sqnorm, max_norm, lr, b1, b2, eps, wd, step):

@@ -215,3 +215,93 @@ def test_ddim_unconditional_and_default_steps_vs_oracle():
     with torch.no_grad():
         r0 = R.ddim_sample(refc, 1e-4, 0.02, cfg["T"], xT, lab, 2.5, 10)
     assert torch.allclose(y0, r0, atol=2e-4), float((y0 - r0).abs().max())
+
+
+def _clone_net(cls, cfg, src, **kw):
+    n = cls(compute_dtype=torch.float32, **kw, **cfg)
+    n.load_state_dict(src.state_dict())
+    return n
+
+
+def test_flat_adamw_skips_never_used_parameters_like_torch():
+    """torch.optim.AdamW skips a parameter whose grad is None: no weight decay, no state.  The unconditional model's
+    cond_proj.* are such parameters (ModelCondition.py:199-200); FlatAdamW must leave them bit-identical, and update
+    everything else like clip_grad_norm_ + AdamW."""
+    from hdiff_b200.optim import FlatAdamW
+    cfg = dict(T=20, ch=32, ch_mult=[1, 2], attn=[1], num_res_blocks=1, dropout=0.0)
+    torch.manual_seed(3)
+    a = UNetU(compute_dtype=torch.float32, **cfg)
+    b = _clone_net(UNetU, cfg, a)
+    before = {k: v.clone() for k, v in a.state_dict().items()}
+    oa = FlatAdamW(a, lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0)
+    ob = torch.optim.AdamW(b.parameters(), lr=1e-3, weight_decay=1e-2)
+    x, t = torch.randn(2, 3, 8, 8), torch.tensor([3, 11])
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    for _ in range(3):
+        oa.zero_grad(); ob.zero_grad()
+        (a(x, t) ** 2).sum().backward()
+        for k in pa:                                  # the SAME gradients for both optimisers: Adam normalises, so the rounding
+            pb[k].grad = None if pa[k].grad is None else pa[k].grad.detach().clone()   # noise of exactly-zero gradients would flip signs
+        oa.step()
+        torch.nn.utils.clip_grad_norm_([p for p in b.parameters() if p.grad is not None], 1.0)
+        ob.step()
+    for k in pa:
+        if "cond_proj" in k:
+            assert pa[k].grad is None and torch.equal(pa[k].detach(), before[k]), k          # untouched: no decay
+        assert torch.allclose(pa[k].detach(), pb[k].detach(), rtol=2e-5, atol=2e-7), (k, float((pa[k] - pb[k]).abs().max()))
+    # an lr scheduler drives param_groups, as in TrainCondition.py:41-44
+    oa.param_groups[0]["lr"] = 5e-4
+    assert oa.lr == 5e-4
+
+
+def test_flat_adamw_uses_accumulated_gradients():
+    """Two micro-batches without zero_grad: autograd sums into the first gradient buffer; FlatAdamW must step on the SUM
+    (it used to read only the last backward's buffer)."""
+    from hdiff_b200.optim import FlatAdamW
+    cfg = dict(T=20, ch=32, ch_mult=[1, 1], attn=[], num_res_blocks=1, dropout=0.0)
+    torch.manual_seed(4)
+    a = UNetC(num_labels=3, compute_dtype=torch.float32, **cfg)
+    b = _clone_net(UNetC, cfg, a, num_labels=3)
+    oa = FlatAdamW(a, lr=1e-3, weight_decay=0.0, max_grad_norm=0.5)
+    ob = torch.optim.AdamW(b.parameters(), lr=1e-3, weight_decay=0.0)
+    xs = [torch.randn(1, 3, 8, 8) for _ in range(2)]
+    t, lab = torch.tensor([7]), torch.tensor([2])
+    for x in xs:
+        (a(x, t, lab) ** 2).sum().backward()
+    first = None
+    for x in xs:                                      # reference sum, formed by hand from two separate backward passes
+        for p in b.parameters():
+            p.grad = None
+        (b(x, t, lab) ** 2).sum().backward()
+        cur = [None if p.grad is None else p.grad.clone() for p in b.parameters()]
+        first = cur if first is None else [u if v is None else v if u is None else u + v for u, v in zip(first, cur)]
+    for p, g, q in zip(b.parameters(), first, a.parameters()):
+        assert (g is None) == (q.grad is None)
+        if g is not None:
+            assert torch.allclose(q.grad, g, rtol=1e-4, atol=1e-6)            # a accumulated the sum of the two micro-batches
+        p.grad = None if q.grad is None else q.grad.detach().clone()          # same gradients into both optimisers
+    oa.step()
+    torch.nn.utils.clip_grad_norm_(b.parameters(), 0.5)
+    ob.step()
+    for (k, p), q in zip(a.named_parameters(), b.parameters()):
+        assert torch.allclose(p.detach(), q.detach(), rtol=2e-5, atol=2e-7), k
+
+
+def test_ddim_argument_errors_are_explicit():
+    sa = GaussianDiffusionSampler(torch.nn.Identity(), 1e-4, 0.02, 1000)
+    x = torch.randn(1, 3, 4, 4)
+    with pytest.raises(ValueError, match="ddim_step"):
+        sa(x, ddim=True)                                   # the reference divides 1000 / None here (Diffusion.py:246)
+    with pytest.raises(ValueError, match="alphas_bar"):
+        sa(x, ddim=True, ddim_step=1000)                   # stride 1 reads alphas_bar[T] (Diffusion.py:251)
+
+
+def test_live_reference_checkpoint_keys_are_rejected_with_a_clear_message():
+    """A checkpoint of the reference's live MHA UNet carries attn.in_proj_weight / attn.out_proj.* keys; loading it into the
+    AttnBlock-style model must fail loudly, not drop every attention weight under strict=False (TrainCondition.py:36-38)."""
+    cfg = dict(T=20, ch=32, ch_mult=[1, 1], attn=[0], num_res_blocks=1, dropout=0.0)
+    net = UNetC(num_labels=3, compute_dtype=torch.float32, **cfg)
+    sd = {k: v for k, v in net.state_dict().items() if ".attn." not in k}
+    sd["downblocks.0.attn.in_proj_weight"] = torch.zeros(96, 32)
+    with pytest.raises(RuntimeError, match="MultiheadAttention"):
+        net.load_state_dict(sd, strict=False)

@@ -1,0 +1,181 @@
+"""North-star TRAJECTORY parity on one GPU (BASELINE.json): the CUDA path (bf16) against the oracle (fp32 PyTorch, TF32
+off) from identical weights, seeds and inputs.
+
+  * training loss curve over 200 optimisation steps at the cfg2 resolution (256x256; batch 4 — the oracle materialises the
+    [S,S] attention scores, 1 GB per image per block): criterion below;
+  * the same with dropout 0.1 (what bench.py times): the two paths draw DIFFERENT dropout masks (torch's Philox stream vs
+    the kernels' counter hash), so the comparison is statistical;
+  * fixed-noise 1000-step classifier-free-guidance sampling (w = 1.8) on a network that was first TRAINED for a few hundred
+    steps, so that the samples are not saturated at +-1 and the PSNR measures 2000 network evaluations rather than the
+    agreement of clipped signs: PSNR >= 40 dB.
+
+Loss-curve criterion.  north_star: "training loss curves within 1 % over 200 steps".  One step's loss is a single draw
+of (t, noise) per image: with the same seeds both paths see the same draw, and the curve falls by two orders of magnitude
+over the run, so a step whose loss happens to be small turns a fixed absolute difference into a large relative one.  The
+test therefore asserts (i) EVERY step within 1 % of the oracle's loss plus 0.1 % of the curve's starting value (the absolute
+floor only matters for those low-loss steps), (ii) the 10-step running mean within 1 % everywhere, and reports the raw
+per-step maximum next to them (written to gpurun_out/parity_trajectory.json when that directory exists).
+"""
+import json
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.slow]
+
+from oracle import ref_torch as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = dict(T=1000, ch=64, ch_mult=[1, 2, 2, 2], attn=[1], num_res_blocks=2)
+STEPS = int(os.environ.get("HDIFF_TRAJ_STEPS", "200"))
+RES = int(os.environ.get("HDIFF_TRAJ_RES", "256"))
+BATCH = int(os.environ.get("HDIFF_TRAJ_BATCH", "4"))
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    import hdiff_b200.ops as hops
+    hops.set_backend(None)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.cuda.empty_cache()
+
+
+def _record(key, value):
+    d = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    p = os.path.join(d, "parity_trajectory.json")
+    rec = {}
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                rec = json.load(f)
+        except Exception:
+            rec = {}
+    rec[key] = value
+    with open(p, "w") as f:
+        json.dump(rec, f, indent=1)
+
+
+def _pair(dropout, num_labels=None, seed=0):
+    from hdiff_b200.diffusion.Model import UNet as UNetU
+    from hdiff_b200.DiffusionFreeGuidence.ModelCondition import UNet as UNetC
+    dev = torch.device("cuda")
+    torch.manual_seed(seed)
+    ref = R.UNet(num_labels=num_labels, dropout=dropout, **CFG)
+    net = UNetU(dropout=dropout, **CFG) if num_labels is None else UNetC(num_labels=num_labels, dropout=dropout, **CFG)
+    net.load_state_dict(ref.state_dict())
+    return net.to(dev), ref.to(dev)
+
+
+def _curves(dropout, steps, res, batch):
+    from hdiff_b200.diffusion.Diffusion import GaussianDiffusionTrainer
+    dev = torch.device("cuda")
+    net, ref = _pair(dropout)
+    net.train(); ref.train()
+    tr, rtr = GaussianDiffusionTrainer(net, 1e-4, 0.02, 1000).to(dev), R.GaussianDiffusionTrainer(ref, 1e-4, 0.02, 1000).to(dev)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-4, weight_decay=1e-4)
+    torch.manual_seed(1)
+    data = [torch.rand(batch, 3, res, res, device=dev) * 2 - 1 for _ in range(8)]
+    mine, theirs = [], []
+    for s in range(steps):
+        x = data[s % len(data)]
+        torch.manual_seed(1000 + s)                       # same (t, noise) draw for both paths
+        mine.append(float(R.train_step(tr, opt, x).detach()))
+        torch.manual_seed(1000 + s)
+        theirs.append(float(R.train_step(rtr, ropt, x).detach()))
+    return mine, theirs
+
+
+def _window(v, w=10):
+    return [sum(v[i:i + w]) / w for i in range(0, len(v) - w + 1)]
+
+
+def test_loss_curve_200_steps_dropout0_within_1_percent():
+    mine, theirs = _curves(0.0, STEPS, RES, BATCH)
+    rel = [abs(a - b) / abs(b) for a, b in zip(mine, theirs)]
+    floor = 1e-3 * theirs[0]
+    sm, st = _window(mine), _window(theirs)
+    rel_w = [abs(a - b) / abs(b) for a, b in zip(sm, st)]
+    worst = max(range(len(rel)), key=lambda i: rel[i])
+    rec = {"steps": STEPS, "resolution": RES, "batch": BATCH, "dropout": 0.0, "max_rel_dev_per_step": max(rel),
+           "mean_rel_dev_per_step": sum(rel) / len(rel), "steps_over_1pct": sum(r > 0.01 for r in rel),
+           "worst_step": [worst, mine[worst], theirs[worst]], "max_rel_dev_10step_mean": max(rel_w),
+           "first": [mine[0], theirs[0]], "last": [mine[-1], theirs[-1]],
+           "criterion": "every step: |a-b| <= 1% b + 0.1% b[0]; 10-step mean within 1%",
+           "curve_ours_every10": mine[::10], "curve_oracle_every10": theirs[::10]}
+    _record("loss_curve_dropout0", rec)
+    assert theirs[-1] < 0.2 * theirs[0], "the run must actually train (curve falls)"
+    bad = [(i, a, b) for i, (a, b) in enumerate(zip(mine, theirs)) if abs(a - b) > 0.01 * abs(b) + floor]
+    assert not bad, (bad[:5], rec["max_rel_dev_per_step"])
+    assert max(rel_w) <= 0.01, max(rel_w)
+
+
+def test_loss_curve_200_steps_dropout01_statistical():
+    """dropout 0.1 (the benchmark's setting).  The masks differ between the two implementations, so single steps differ by
+    the dropout noise itself; what must agree is the curve: the mean loss over each 20-step window within 5 % (the oracle's
+    own window means move by about that much between two dropout seeds), and the mean over the last 100 steps within 2 %."""
+    mine, theirs = _curves(0.1, STEPS, RES, BATCH)
+    W = 20
+    sm, st = _window(mine, W), _window(theirs, W)
+    rel_w = [abs(a - b) / abs(b) for a, b in zip(sm, st)]
+    h = len(mine) // 2
+    tail = abs(sum(mine[h:]) - sum(theirs[h:])) / abs(sum(theirs[h:]))
+    _record("loss_curve_dropout01", {"steps": STEPS, "resolution": RES, "batch": BATCH, "dropout": 0.1,
+                                     "max_rel_dev_20step_mean": max(rel_w), "rel_dev_mean_last_half": tail,
+                                     "first": [mine[0], theirs[0]], "last": [mine[-1], theirs[-1]],
+                                     "curve_ours_every10": mine[::10], "curve_oracle_every10": theirs[::10]})
+    assert theirs[-1] < 0.2 * theirs[0]
+    assert max(rel_w) <= 0.05, max(rel_w)
+    assert tail <= 0.02, tail
+
+
+def _psnr(a, b):
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return float("inf") if mse == 0 else 10 * math.log10(4.0 / mse)      # images live in [-1, 1]: peak-to-peak 2
+
+
+def test_fixed_noise_1000_step_cfg_sampling_psnr_on_a_trained_network():
+    from hdiff_b200.DiffusionFreeGuidence.DiffusionCondition import GaussianDiffusionSampler
+    dev = torch.device("cuda")
+    res, B, T = int(os.environ.get("HDIFF_TRAJ_SAMPLE_RES", "64")), 2, int(os.environ.get("HDIFF_TRAJ_SAMPLE_T", "1000"))
+    net, ref = _pair(0.0, num_labels=10, seed=2)
+    # ---- train the ORACLE for a few hundred steps on smooth synthetic images (class = colour cast), copy the weights ----
+    ref.train()
+    rtr = R.GaussianDiffusionTrainer(ref, 1e-4, 0.02, 1000).to(dev)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=2e-4, weight_decay=1e-4)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, res, device=dev), torch.linspace(-1, 1, res, device=dev), indexing="ij")
+    for s in range(int(os.environ.get("HDIFF_TRAJ_PRETRAIN", "400"))):
+        lab = torch.randint(0, 10, (16,), generator=g, device=dev) + 1
+        ph = torch.rand(16, 3, 1, 1, generator=g, device=dev) * 6.28
+        fr = 1 + 3 * torch.rand(16, 3, 1, 1, generator=g, device=dev)
+        x = 0.6 * torch.sin(fr * xx + ph) * torch.cos(fr * yy - ph) + 0.3 * ((lab.view(-1, 1, 1, 1).float() - 5.5) / 5.5)
+        if s % 10 == 0:
+            lab = torch.zeros_like(lab)                               # label dropout (TrainCondition.py:57-58)
+        R.train_step(rtr, ropt, x.clamp(-1, 1), lab)
+    net.load_state_dict(ref.state_dict())
+    net.eval(); ref.eval()
+    xT = torch.randn(B, 3, res, res, device=dev)
+    lab = torch.tensor([3, 8], device=dev)
+    outs = {}
+    for graph in (True, False):
+        smp = GaussianDiffusionSampler(net, 1e-4, 0.02, T, w=1.8).to(dev)
+        smp.use_cuda_graph = graph
+        torch.manual_seed(3)
+        outs[graph] = smp(xT, lab)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        r0 = R.GaussianDiffusionSampler(ref, 1e-4, 0.02, T, w=1.8).to(dev)(xT, lab)
+    clipped = float((r0.abs() >= 1.0).float().mean())
+    rec = {"T": T, "w": 1.8, "resolution": res, "batch": B, "psnr_db_graph": _psnr(outs[True], r0),
+           "psnr_db_eager": _psnr(outs[False], r0), "graph_vs_eager_max_abs": float((outs[True] - outs[False]).abs().max()),
+           "max_abs_diff": float((outs[True] - r0).abs().max()), "clipped_frac_oracle": clipped, "out_std": float(r0.std())}
+    _record("sampling_psnr", rec)
+    assert clipped < 0.5, f"sample saturated ({clipped:.3f} of the pixels at +-1): the PSNR would measure clipped signs"
+    assert rec["psnr_db_graph"] >= 40.0 and rec["psnr_db_eager"] >= 40.0, rec
