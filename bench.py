@@ -1,17 +1,28 @@
 """bench.py — DDPM UNet training throughput (images/s) at 256x256 on N B200s, the metric BASELINE.json names.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 our arm (hdiff_b200 CUDA path)
-    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  reference arm: the fp32 PyTorch path on host cores
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  reference arm: the reference's fp32 PyTorch path on host cores
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
 
-A step is one pass of the hot path over one batch: GaussianDiffusionTrainer.forward(x_0) -> `.sum()/1000.` ->
-backward -> clip_grad_norm_(1.0) -> AdamW (diffusion/Train.py:49-55 of the reference).  Workload at every N:
-BASELINE.json configs[1] (UNet ch=64 ch_mult=[1,2,2,2] attn=[1] num_res_blocks=2 T=1000 dropout=0.1, 256x256 RGB,
-batch 32 per GPU, bf16 compute with fp32 master weights, synthetic data, random-init weights).
+A step is one pass of the hot path over one batch.
+  N = 1: BASELINE.json configs[1] — unconditional UNet ch=64 ch_mult=[1,2,2,2] attn=[1] num_res_blocks=2 T=1000 dropout=0.1,
+         256x256 RGB, batch 32, bf16 compute / fp32 master weights:
+         GaussianDiffusionTrainer.forward(x_0) -> `.sum()/1000.` -> backward -> clip_grad_norm_(1.0) -> AdamW (diffusion/Train.py:49-55).
+  N > 1: BASELINE.json configs[2] — the CONDITIONAL UNet (num_labels=10) of the same size, labels+1, whole-batch label dropout
+         with a per-rank host coin (p = 0.1), `.sum()/b**2` (DiffusionFreeGuidence/TrainCondition.py:53-63), batch 32 per GPU,
+         data parallel over NCCL.
+Synthetic data, random-init weights.
 
-One JSON line on stdout (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step driven with pinned HOST
-batches (host->device copy of x_0 and device->host read of the loss inside the timed region).
-`oracle/` is imported only by the cpu_baseline leg and by `--impl reference`.
+One JSON line on stdout (rank 0):
+  value      timed region = K steps with inputs resident in HBM, NO per-launch instrumentation inside it;
+  e2e        the same step driven with pinned HOST batches (host->device copy of x_0 [and labels], device->host read of the loss);
+  roofline / kernel_families   from a SEPARATE profiling pass after the timed ones (CUDA events around every launch);
+  sampling   the second half of the metric: the full 1000-step CFG chain (w = 1.8) on 8 images per GPU through
+             GaussianDiffusionSampler.forward, its own roofline and CPU baseline;
+  gpu_reference  (N = 1) the same training step by stock PyTorch on the same B200: the oracle in fp32 (TF32 off) at the largest
+             batch that fits, and under bf16 autocast with F.scaled_dot_product_attention at batch 32;
+  cpu_baseline   (N = 1) the reference's CPU path on the host cores, bounded sample.
+`oracle/` is imported only by the cpu_baseline / gpu_reference legs and by `--impl reference`.
 """
 from __future__ import annotations
 
@@ -28,9 +39,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 CFG2 = dict(T=1000, ch=64, ch_mult=[1, 2, 2, 2], attn=[1], num_res_blocks=2, dropout=0.1)
+NUM_LABELS = 10
 BETA_1, BETA_T = 1e-4, 0.02
 METRIC = "ddpm_train_images_per_sec_256"
 UNIT = "images/s"
+FWD_GFLOP_PER_IMAGE_256 = 488.0          # conv 212.6 + attention 275.4 GFLOP forward per image at 256x256
 
 
 def _peaks():
@@ -90,28 +103,100 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle (fp32 PyTorch restatement of the reference path) on host cores
+# reference arm / cpu_baseline: the reference's fp32 PyTorch path on host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, res, batch, threads=None):
-    """Times `steps` training steps of the reference fp32 path on the host.  Returns (images/s, seconds per step)."""
+def _reference_model(cond, dropout=None):
+    """(net, trainer class, sampler class, kind): the reference's OWN classes when its sources are reachable (/root/reference in
+    the build container, oracle/_ref on the GPU box — `oracle/make_ref.py` puts them there), else the restatement."""
+    from oracle import ref_loader, ref_torch as R
+    cfg = dict(CFG2)
+    if dropout is not None:
+        cfg["dropout"] = dropout
+    if ref_loader.available():
+        net = ref_loader.assemble_unet(num_labels=NUM_LABELS if cond else None, **cfg)
+        dc = ref_loader.diffusion_condition()
+        return net, _RefTrainer(dc), dc.GaussianDiffusionSampler, "reference"
+    return R.UNet(num_labels=NUM_LABELS if cond else None, **cfg), R.GaussianDiffusionTrainer, R.GaussianDiffusionSampler, "port"
+
+
+class _RefTrainer:
+    """GaussianDiffusionTrainer of DiffusionCondition.py:19-46 takes (x_0, labels); the unconditional twin
+    (diffusion/Diffusion.py:304-314, commented there) is the same algorithm without labels — driven here through a
+    one-argument model adapter so that the reference class itself runs."""
+
+    def __init__(self, dc):
+        self.dc = dc
+
+    def __call__(self, net, beta_1, beta_T, T):
+        import torch.nn as nn
+        dc = self.dc
+
+        class Uncond(nn.Module):
+            def __init__(self, m):
+                super().__init__()
+                self.m = m
+
+            def forward(self, x, t, labels):
+                return self.m(x, t) if labels is None else self.m(x, t, labels)
+
+        tr = dc.GaussianDiffusionTrainer(Uncond(net), beta_1, beta_T, T)
+        tr.hd_net = net
+        return tr
+
+
+def cpu_reference_steps(steps, warmup, res, batch, threads=None, cond=False):
+    """Times `steps` training steps of the reference fp32 path on the host.  Returns (images/s, s per step, threads, kind)."""
+    import numpy as np
     import torch
-    from oracle import ref_torch as R                    # CPU baseline only: the thing timed here is the reference path
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    net = R.UNet(**CFG2)
-    tr = R.GaussianDiffusionTrainer(net, BETA_1, BETA_T, CFG2["T"])
+    net, Trainer, _, kind = _reference_model(cond)
+    tr = Trainer(net, BETA_1, BETA_T, CFG2["T"])
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
     x = torch.rand(batch, 3, res, res) * 2 - 1
+    rng = np.random.RandomState(0)
     ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        R.train_step(tr, opt, x)
+        opt.zero_grad()
+        if cond:
+            labels = torch.randint(0, NUM_LABELS, (batch,)) + 1
+            if rng.rand() < 0.1:
+                labels = torch.zeros_like(labels)
+            loss = tr(x, labels).sum() / batch ** 2.
+        else:
+            loss = (tr(x, None) if kind == "reference" else tr(x)).sum() / 1000.
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
     ts.sort()
     med = ts[len(ts) // 2]
-    return batch / med, med, threads
+    return batch / med, med, threads, kind
+
+
+def cpu_reference_sampling(n_steps, res, batch, threads=None):
+    """`n_steps` of the 1000 CFG ancestral steps (2 UNet evaluations each) of the reference on the host, extrapolated.
+    Returns (images/s for the full chain, s per sampler step, threads, kind)."""
+    import torch
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net, _, Sampler, kind = _reference_model(True, dropout=0.0)
+    net.eval()
+    smp = Sampler(net, BETA_1, BETA_T, n_steps, w=1.8)
+    x = torch.randn(batch, 3, res, res)
+    labels = torch.arange(batch) % NUM_LABELS + 1
+    import contextlib
+    import io
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):   # the reference prints the step index (DiffusionCondition.py:88)
+        Sampler(net, BETA_1, BETA_T, 2, w=1.8)(x, labels)             # warm-up: a 2-step chain
+        t0 = time.perf_counter()
+        smp(x, labels)
+        sec = (time.perf_counter() - t0) / n_steps
+    return batch / (sec * CFG2["T"]), sec, threads, kind
 
 
 def run_reference(args):
@@ -119,28 +204,100 @@ def run_reference(args):
     if rank != 0:
         return
     res, batch = args.res, args.ref_batch
-    v, sec, threads = cpu_reference_steps(args.steps, max(1, min(args.warmup, 1)), res, batch)
-    sample = (f"{args.steps} timed training steps (median) of the fp32 PyTorch reference path on the host, batch {batch} at {res}x{res} "
-              f"(the reference materialises [S,S] attention scores: ~1 GB per image per block at S=16384), reported per image")
+    cond = args.gpus > 1
+    v, sec, threads, kind = cpu_reference_steps(args.steps, max(1, min(args.warmup, 1)), res, batch, cond=cond)
+    what = "the reference's own classes (oracle/ref_loader.assemble_unet + DiffusionCondition.GaussianDiffusionTrainer)" \
+        if kind == "reference" else "the oracle restatement (oracle/ref_torch.py; the reference sources are not reachable here)"
+    sample = (f"{args.steps} timed training steps (median) of the fp32 PyTorch reference path on the host — {what} — batch {batch} at "
+              f"{res}x{res} (the reference materialises [S,S] attention scores: ~1 GB per image per block at S=16384), reported per image")
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"cfg2 DDPM UNet ch=64 [1,2,2,2] attn=[1] nrb=2 T=1000 dropout=0.1 train step, {res}x{res}",
-                      "global_batch": batch, "resolution": res},
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "config": {"workload": _workload(cond, res), "global_batch": batch, "resolution": res},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
+
+
+def _workload(cond, res):
+    if cond:
+        return (f"cfg3 conditional DDPM UNet (num_labels=10) ch=64 [1,2,2,2] attn=[1] nrb=2 T=1000 dropout=0.1, label-dropout CFG train step "
+                f"(labels+1, whole-batch drop p=0.1, trainer fwd + sum/b^2 + bwd + clip 1.0 + AdamW), {res}x{res}")
+    return (f"cfg2 DDPM UNet ch=64 [1,2,2,2] attn=[1] nrb=2 T=1000 dropout=0.1 train step "
+            f"(trainer fwd + sum/1000 + bwd + clip 1.0 + AdamW), {res}x{res}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# same-GPU reference: stock PyTorch (cuDNN / cuBLAS) running the oracle
+# ---------------------------------------------------------------------------------------------------
+def gpu_reference(dev, res, steps=3):
+    """cfg2 'vs reference fp32': the oracle's training step on this GPU in fp32 with TF32 off at the largest batch that fits
+    (it materialises the [S,S] attention scores), and the fastest stock-PyTorch form of the same step (bf16 autocast,
+    F.scaled_dot_product_attention, batch 32).  Reported, not the target."""
+    import torch
+    from oracle import ref_torch as R
+    out = {}
+
+    def run(batch, autocast, sdpa):
+        torch.manual_seed(0)
+        R.AttnBlock.use_sdpa = sdpa
+        net = R.UNet(**CFG2).to(dev).train()
+        tr = R.GaussianDiffusionTrainer(net, BETA_1, BETA_T, CFG2["T"]).to(dev)
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+        x = torch.rand(batch, 3, res, res, device=dev) * 2 - 1
+        ts = []
+        for i in range(steps + 1):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                R.train_step(tr, opt, x)
+            e1.record()
+            torch.cuda.synchronize()
+            if i:
+                ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        for b in (8, 4, 2, 1):
+            try:
+                ms = run(b, False, False)
+                out["fp32"] = {"value": b / (ms * 1e-3), "unit": UNIT, "batch": b, "ms_per_step": ms,
+                               "what": "oracle/ref_torch.py (restatement of the reference modules) in fp32, TF32 off, cuDNN/cuBLAS, "
+                                       "largest batch of (8, 4, 2, 1) that fits with materialised [S,S] attention scores"}
+                break
+            except torch.cuda.OutOfMemoryError:
+                torch.cuda.empty_cache()
+        try:
+            ms = run(32, True, True)
+            out["bf16_sdpa"] = {"value": 32 / (ms * 1e-3), "unit": UNIT, "batch": 32, "ms_per_step": ms,
+                                "what": "the same modules under torch.autocast(bfloat16) with F.scaled_dot_product_attention in AttnBlock "
+                                        "(cuDNN convolutions + the library flash attention), batch 32: the fastest stock-PyTorch form of the step"}
+        except Exception as e:                           # noqa: BLE001  (reported, never fatal)
+            out["bf16_sdpa"] = {"unavailable": repr(e)[:200]}
+    finally:
+        R.AttnBlock.use_sdpa = False
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     from hdiff_b200.diffusion.Model import UNet
+    from hdiff_b200.DiffusionFreeGuidence.ModelCondition import UNet as CondUNet
     from hdiff_b200.diffusion.Diffusion import GaussianDiffusionTrainer
+    from hdiff_b200.DiffusionFreeGuidence.DiffusionCondition import GaussianDiffusionSampler
     from hdiff_b200.optim import FlatAdamW
     from hdiff_b200 import parallel
     import hdiff_b200.ops as hops
@@ -158,8 +315,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, res = args.batch, args.res
+    cond = world > 1 or args.cond                          # N > 1: configs[2], the conditional model with label dropout
     torch.manual_seed(0)                                   # identical replicas
-    net = UNet(**CFG2).to(dev)
+    net = (CondUNet(num_labels=NUM_LABELS, **CFG2) if cond else UNet(**CFG2)).to(dev)
     net.train()
     if world > 1:
         parallel.enable_data_parallel(net)
@@ -167,21 +325,33 @@ def run_ours(args):
     opt = FlatAdamW(net, lr=1e-4, weight_decay=1e-4, max_grad_norm=1.0)
     ops = hops.get()
     torch.manual_seed(1000 + rank)                         # per-rank data and RNG stream
+    coin = np.random.RandomState(1000 + rank)              # the reference's per-process host coin (TrainCondition.py:57)
     n_pool = 6                                             # 6 x 25 MB of distinct batches > the 126 MB L2
     host_pool = [(torch.rand(B, 3, res, res) * 2 - 1).pin_memory() for _ in range(n_pool)]
+    host_lab = [torch.randint(0, NUM_LABELS, (B,)).pin_memory() for _ in range(n_pool)]
     dev_pool = [h.to(dev) for h in host_pool]
+    dev_lab = [h.to(dev) for h in host_lab]
+
+    def loss_of(x, labels):
+        if not cond:
+            return trainer(x).sum() / 1000.
+        labels = labels + 1
+        if coin.rand() < 0.1:
+            labels = torch.zeros_like(labels)
+        return trainer(x, labels).sum() / B ** 2.
 
     def step_resident(i):
         opt.zero_grad()
-        loss = trainer(dev_pool[i % n_pool]).sum() / 1000.
+        loss = loss_of(dev_pool[i % n_pool], dev_lab[i % n_pool])
         loss.backward()
         opt.step()
         return loss
 
     def step_e2e(i):
         x = host_pool[i % n_pool].to(dev, non_blocking=True)
+        lab = host_lab[i % n_pool].to(dev, non_blocking=True) if cond else None
         opt.zero_grad()
-        loss = trainer(x).sum() / 1000.
+        loss = loss_of(x, lab)
         loss.backward()
         opt.step()
         return float(loss.item())                          # device -> host read of the step's result
@@ -210,17 +380,19 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     l0 = ops.launches
-    ops.prof = {}                                          # per-launch CUDA events on the launching stream
-    ms = timed(step_resident, args.steps)
-    prof, ops.prof = ops.prof, None
+    ms = timed(step_resident, args.steps)                  # the `value` region: no per-launch events, no host reads
     launches = ops.launches - l0
     clk = clocks.stop() if rank == 0 else None
     # ---- end-to-end through the public API with host batches ----
     step_e2e(0)
     ms_e2e = timed(step_e2e, args.steps)
     loss_val = step_e2e(0)
+    # ---- separate profiling pass: CUDA events around every launch, on the launching stream ----
+    n_prof = max(1, min(args.steps, args.profile_steps))
+    ops.prof = {}
+    timed(step_resident, n_prof)
+    prof, ops.prof = ops.prof, None
 
-    # ---- roofline of the dominant kernel family (device time from the events recorded above) ----
     fam = {}
     for name, lst in prof.items():
         t = sum(a.elapsed_time(b) for a, b, _ in lst)
@@ -234,61 +406,77 @@ def run_ours(args):
     roof, fam_out = None, {}
     tot = sum(f["ms"] for f in fam.values()) or 1.0
     for name, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
-        tensor = name.startswith(("conv", "wgrad", "attn"))
+        tensor = name.startswith(("conv", "wgrad", "attn", "mha"))
         ach = f["work"] / (f["ms"] * 1e-3) / (1e12 if tensor else 1e9) if f["ms"] > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"] if tensor else peaks["hbm_gbs"]
-        fam_out[name] = {"ms_per_step": f["ms"] / args.steps, "launches_per_step": f["launches"] / args.steps,
+        fam_out[name] = {"ms_per_step": f["ms"] / n_prof, "launches_per_step": f["launches"] / n_prof,
                          "achieved": ach, "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak}
         if roof is None:
             roof = {"kernel": name, "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak,
                     "traffic": traffic.get(name, {}).get("traffic_bytes"), "traffic_detail": traffic.get(name),
                     "peak_source": peaks["source"] + (" sustained bf16 (kernel timed inside a long step)" if tensor else " copy bandwidth"),
-                    "share_of_timed_kernels": f["ms"] / tot}
-    # ---- CFG sampling (the second half of BASELINE.json's metric): configs[3] shape, a bounded number of the 1000 steps ----
+                    "share_of_timed_kernels": f["ms"] / tot,
+                    "timed_in": f"separate profiling pass of {n_prof} step(s) after the timed regions (per-launch CUDA events)"}
+    step_tflops = 3 * FWD_GFLOP_PER_IMAGE_256 * (res / 256.) ** 2 * B / (ms / args.steps)      # GFLOP / ms = TFLOP/s (attention share scales as res^4: 256 only)
+
+    # ---- CFG sampling (the second half of BASELINE.json's metric): configs[3] — the full 1000-step chain ----
     sampling = None
     if args.sample_steps > 0:
         del trainer, opt, dev_pool
         net._state = None
         del net
         torch.cuda.empty_cache()
-        from hdiff_b200.DiffusionFreeGuidence.ModelCondition import UNet as CondUNet
-        from hdiff_b200.DiffusionFreeGuidence.DiffusionCondition import GaussianDiffusionSampler
         torch.manual_seed(0)
         cfg = dict(CFG2); cfg["dropout"] = 0.0
-        snet = CondUNet(num_labels=10, **cfg).to(dev)
+        snet = CondUNet(num_labels=NUM_LABELS, **cfg).to(dev)
         snet.eval()
-        sampler = GaussianDiffusionSampler(snet, BETA_1, BETA_T, CFG2["T"], w=1.8).to(dev)
+        T_s = args.sample_steps
+        sampler = GaussianDiffusionSampler(snet, BETA_1, BETA_T, T_s, w=1.8).to(dev)
         Bs = args.sample_batch
         torch.manual_seed(2000 + rank)
-        x = torch.randn(Bs, 3, res, res, device=dev)
-        labels = (torch.arange(Bs, device=dev) + rank * Bs) % 10 + 1
-        step = torch.full((1,), CFG2["T"] - 1, dtype=torch.int32, device=dev)
-        nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        sampler.run_steps(x, labels, step, nan_flag, 3)                     # warm-up (includes graph capture cost once)
+        xT = torch.randn(Bs, 3, res, res, device=dev)
+        labels = (torch.arange(Bs, device=dev) + rank * Bs) % NUM_LABELS + 1
+        warm = GaussianDiffusionSampler(snet, BETA_1, BETA_T, 4, w=1.8).to(dev)
+        warm(xT, labels)                                                    # warm-up: a 4-step chain (lazy state, first graph capture)
         barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l1 = ops.launches
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        sampler.run_steps(x, labels, step, nan_flag, args.sample_steps)
+        x0 = sampler(xT, labels)                                            # the public call: T steps, graph capture once, NaN check
         s1.record()
         barrier()
         sms = torch.tensor([s0.elapsed_time(s1)], device=dev)
         if world > 1:
             dist.all_reduce(sms, op=dist.ReduceOp.MAX)
-        per_step = float(sms.item()) / args.sample_steps
-        sampling = {"metric": "cfg_sampling_images_per_sec_256", "value": world * Bs / (per_step * 1e-3 * CFG2["T"]), "unit": UNIT,
-                    "ms_per_sampler_step": per_step, "sampler_steps_timed": args.sample_steps,
-                    "note": f"{args.sample_steps} of the {CFG2['T']} ancestral steps timed (each = one 2B-batch conditional+null UNet forward "
-                            "+ fused CFG/posterior update) as replays of the step's CUDA graph (captured once during warm-up, as it is once per 1000-step "
-                            "chain), extrapolated to the full chain",
-                    "ddim100_images_per_s": world * Bs / (per_step * 1e-3 * 100),
+        chain_s = float(sms.item()) * 1e-3
+        per_step = chain_s / T_s
+        full = T_s == CFG2["T"]
+        tf = 2 * Bs * FWD_GFLOP_PER_IMAGE_256 * (res / 256.) ** 2 / (per_step * 1e3)             # 2B forward passes per step
+        sampling = {"metric": "cfg_sampling_images_per_sec_256", "value": world * Bs / (per_step * CFG2["T"]), "unit": UNIT,
+                    "chain_seconds": chain_s, "ms_per_sampler_step": per_step * 1e3, "sampler_steps_timed": T_s,
+                    "note": ("the FULL 1000-step ancestral chain through GaussianDiffusionSampler.forward" if full else
+                             f"{T_s} of the 1000 ancestral steps (extrapolated)") +
+                            " (each step = one 2B-batch conditional+null UNet forward + fused CFG/posterior update; the step's CUDA graph is "
+                            "captured once inside the call and replayed)",
+                    "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                 "frac": tf / peaks["bf16_tflops_sustained"],
+                                 "work": f"2 x {Bs} forward passes x {FWD_GFLOP_PER_IMAGE_256} GFLOP algorithmic per sampler step"},
+                    "ddim100_images_per_s": world * Bs / (per_step * 100),
                     "ddim_note": "the same step (same launches; another coefficient table) run as the 100-step deterministic DDIM sampler "
                                  "of the hybrid pipeline (sampler(x_T, labels, ddim=True, ddim_step=100)); derived from the step time above",
                     "batch_per_gpu": Bs, "global_batch": world * Bs, "guidance_w": 1.8, "cuda_graph": bool(sampler.use_cuda_graph),
-                    "nan_flag": int(nan_flag.item())}
+                    "launches": ops.launches - l1, "out_abs_max": float(x0.abs().max())}
+        del snet, sampler, warm
+        torch.cuda.empty_cache()
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    gpu_ref = None
+    if world == 1 and not args.no_gpu_reference:
+        try:
+            gpu_ref = gpu_reference(dev, res)
+        except Exception as e:                                              # noqa: BLE001
+            gpu_ref = {"unavailable": repr(e)[:300]}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)
@@ -296,23 +484,30 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    h2d = B * 3 * res * res * 4 + (B * 8 if cond else 0)
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
            "data": "synthetic",
-           "config": {"workload": f"cfg2 DDPM UNet ch=64 [1,2,2,2] attn=[1] nrb=2 T=1000 dropout=0.1 train step "
-                                  f"(trainer fwd + sum/1000 + bwd + clip 1.0 + AdamW), {res}x{res}",
+           "config": {"workload": _workload(cond, res),
                       "global_batch": world * B, "per_gpu_batch": B, "resolution": res, "parallelism": f"dp{world}",
                       "l2": f"{n_pool} rotating input batches ({n_pool * B * 3 * res * res * 4 >> 20} MiB) and a multi-GB activation "
                             "working set per step, both larger than the 126 MB L2"},
-           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * B * 3 * res * res * 4, "d2h_bytes_per_step": world * 4,
+           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * 4,
                    "ms_per_step": ms_e2e / args.steps},
            "gpu_launches": launches, "tcgen05_launches_total": ops.tc_launches, "loss": loss_val,
-           "roofline": roof, "kernel_families": fam_out, "clocks": clk, "sampling": sampling}
+           "step_algorithmic_tflops": step_tflops, "step_frac_of_sustained_bf16": step_tflops / peaks["bf16_tflops_sustained"],
+           "roofline": roof, "kernel_families": fam_out, "clocks": clk, "sampling": sampling, "gpu_reference": gpu_ref}
     if world == 1 and not args.no_cpu_baseline:
-        v, sec, threads = cpu_reference_steps(args.cpu_steps, 1, res, args.ref_batch)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+        v, sec, threads, kind = cpu_reference_steps(args.cpu_steps, 1, res, args.ref_batch, cond=cond)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
                                "sample": f"{args.cpu_steps} training steps (median, after 1 warm-up) of the fp32 PyTorch reference path "
-                                         f"(oracle/ref_torch.py) at batch {args.ref_batch}, {res}x{res}, {threads} torch threads; per image"}
+                                         f"({'the reference classes via oracle/ref_loader' if kind == 'reference' else 'oracle/ref_torch.py'}) "
+                                         f"at batch {args.ref_batch}, {res}x{res}, {threads} torch threads; per image"}
+        if sampling is not None and args.cpu_sample_steps > 0:
+            sv, ssec, threads, kind = cpu_reference_sampling(args.cpu_sample_steps, res, 1)
+            sampling["cpu_baseline"] = {"value": sv, "unit": UNIT, "cores": threads, "kind": kind,
+                                        "sample": f"{args.cpu_sample_steps} CFG sampler steps (2 UNet evaluations each, batch 1, {res}x{res}) "
+                                                  f"after a 2-step warm-up chain, {ssec:.2f} s per step, extrapolated to the 1000-step chain"}
     else:
         out["cpu_baseline"] = None
     print(json.dumps(out), flush=True)
@@ -328,10 +523,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (configs[1]: 32)")
     ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--cond", action="store_true", help="run the conditional (cfg3) step at N = 1 too")
     ap.add_argument("--ref-batch", type=int, default=1, help="batch of the CPU reference sample")
     ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-steps", type=int, default=4, help="CFG sampler steps of the CPU baseline (0: skip)")
+    ap.add_argument("--profile-steps", type=int, default=3, help="steps of the separate per-launch profiling pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sample-steps", type=int, default=20, help="ancestral sampler steps timed after the training measurement (0: skip)")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--sample-steps", type=int, default=1000, help="length of the CFG sampling chain timed after training (0: skip)")
     ap.add_argument("--sample-batch", type=int, default=8, help="per-GPU sampling batch (configs[3]: 64 images over 8 GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":

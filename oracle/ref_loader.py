@@ -1,8 +1,9 @@
 """ORACLE support (test infrastructure): import the *unmodified* reference by file path.
 
-Works only where /root/reference exists (the build container).  Nothing on the GPU box may
-call this; it is used by `oracle/make_golden.py` and `tests/test_oracle_vs_reference.py`
-(which skips when the tree is absent) to pin `oracle/ref_torch.py` against the reference.
+Looks in /root/reference (the build container) and then in `oracle/_ref/` (verbatim copies made by
+`oracle/make_ref.py`; git-ignored, shipped to the GPU box with the snapshot).  Used by `oracle/make_golden.py`
+and the tests that pin `oracle/ref_torch.py` against the reference (they skip when neither tree exists), and by
+`bench.py`'s CPU baseline / `--impl reference`, which time the reference's own classes through it.
 
 Facts handled here:
   F3  DiffusionFreeGuidence/ModelCondition.py:289 has a one-token SyntaxError in the unused
@@ -21,7 +22,19 @@ import warnings
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("HDIFF_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """/root/reference in the build container; on the GPU box the verbatim copies that oracle/make_ref.py left in oracle/_ref."""
+    env = os.environ.get("HDIFF_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", os.path.join(_HERE, "_ref")]:
+        if os.path.isfile(os.path.join(cand, "DiffusionFreeGuidence", "DiffusionCondition.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

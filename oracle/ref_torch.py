@@ -101,7 +101,12 @@ class UpSample(nn.Module):
 
 
 class AttnBlock(nn.Module):
-    """Single-head spatial self-attention with residual (ModelCondition.py:92-120)."""
+    """Single-head spatial self-attention with residual (ModelCondition.py:92-120).
+
+    `use_sdpa` (class switch, default off = the reference's arithmetic): bench.py's same-GPU "stock PyTorch" leg swaps
+    the materialised bmm / softmax / bmm for F.scaled_dot_product_attention (same function; the library's flash kernel)."""
+
+    use_sdpa = False
 
     def __init__(self, in_ch):
         super().__init__()
@@ -117,6 +122,9 @@ class AttnBlock(nn.Module):
         q = self.proj_q(h).permute(0, 2, 3, 1).reshape(B, H * W, C)
         k = self.proj_k(h).reshape(B, C, H * W)
         v = self.proj_v(h).permute(0, 2, 3, 1).reshape(B, H * W, C)
+        if AttnBlock.use_sdpa:
+            o = F.scaled_dot_product_attention(q[:, None], k.transpose(1, 2)[:, None], v[:, None], scale=int(C) ** (-0.5))[:, 0]
+            return x + self.proj(o.reshape(B, H, W, C).permute(0, 3, 1, 2))
         w = F.softmax(torch.bmm(q, k) * (int(C) ** (-0.5)), dim=-1)
         h = torch.bmm(w, v).view(B, H, W, C).permute(0, 3, 1, 2)
         return x + self.proj(h)
