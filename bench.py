@@ -240,6 +240,9 @@ def gpu_reference(dev, res, steps=3):
     out = {}
 
     def run(batch, autocast, sdpa):
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
         torch.manual_seed(0)
         R.AttnBlock.use_sdpa = sdpa
         net = R.UNet(**CFG2).to(dev).train()

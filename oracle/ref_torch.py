@@ -123,7 +123,8 @@ class AttnBlock(nn.Module):
         k = self.proj_k(h).reshape(B, C, H * W)
         v = self.proj_v(h).permute(0, 2, 3, 1).reshape(B, H * W, C)
         if AttnBlock.use_sdpa:
-            o = F.scaled_dot_product_attention(q[:, None], k.transpose(1, 2)[:, None], v[:, None], scale=int(C) ** (-0.5))[:, 0]
+            o = F.scaled_dot_product_attention(q.contiguous()[:, None], k.transpose(1, 2).contiguous()[:, None], v.contiguous()[:, None],
+                                               scale=int(C) ** (-0.5))[:, 0]
             return x + self.proj(o.reshape(B, H, W, C).permute(0, 3, 1, 2))
         w = F.softmax(torch.bmm(q, k) * (int(C) ** (-0.5)), dim=-1)
         h = torch.bmm(w, v).view(B, H, W, C).permute(0, 3, 1, 2)
