@@ -24,6 +24,7 @@ PROTOTYPES = {
     "hd_gather_pack": [I, P, P, P, L, P, P],
     "hd_scatter_unpack": [P, P, L, P, P],
     "hd_gn_stats": [I, P, I, P, I, I, L, I, P, P],
+    "hd_gn_v2": [I, I, I, I, L, I],
     "hd_gn_apply": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P],
     "hd_gn_bwd_reduce": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P, P],
     "hd_gn_bwd_apply": [I, P, I, P, I, I, L, I, P, P, P, F, I, F, U64, P, P, P, P, P, P, P, P, P, L, I, I, P],
@@ -51,8 +52,11 @@ PROTOTYPES = {
     "hd_attn_fwd_wide_tc": [P, P, P, I, I, I, P],
     "hd_attn_bwd_wide_tc": [P, P, P, P, P, P, I, I, I, P],
     "hd_attn_bwd_tc_supported": [I, I],
+    "hd_mha_supported": [I, I],
+    "hd_mha_fwd": [I, P, P, P, I, I, I, I, P],
+    "hd_mha_bwd": [I, P, P, P, P, P, P, I, I, I, I, P],
 }
-NON_STATUS = {"hd_conv_tc_supported", "hd_conv_tc_stats_staged", "hd_wgrad_tc_supported", "hd_attn_tc_supported", "hd_attn_bwd_tc_supported", "hd_attn_wide_tc_supported",
+NON_STATUS = {"hd_gn_v2", "hd_mha_supported", "hd_conv_tc_supported", "hd_conv_tc_stats_staged", "hd_wgrad_tc_supported", "hd_attn_tc_supported", "hd_attn_bwd_tc_supported", "hd_attn_wide_tc_supported",
               "hd_wgrad_tc_workspace"}
 
 # lab library only (include/hdiff_b200_lab.h): hardware probes and timing experiments, not part of the product ABI

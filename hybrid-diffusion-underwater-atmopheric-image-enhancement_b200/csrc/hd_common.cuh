@@ -62,30 +62,52 @@ template <bool kFast> __device__ __forceinline__ float hd_swish_grad_t(float x) 
 __device__ __forceinline__ float hd_swish(float x) { return x * hd_sigmoid(x); }
 __device__ __forceinline__ float hd_swish_grad(float x) { float s = hd_sigmoid(x); return s * (1.f + x * (1.f - s)); }
 
-// Counter-based RNG for dropout: one 32-bit hash per PAIR of consecutive elements, 16 uniform bits per element
-// (drop probability resolution 2^-16); the backward pass regenerates the mask from the same (seed, index) instead
-// of storing it.  ~3 integer instructions per element, so the GroupNorm kernels stay HBM-bound with dropout on.
-__host__ __device__ __forceinline__ uint32_t hd_hash_pair(uint64_t seed, uint64_t pair) {
-    uint32_t h = (uint32_t)pair * 0x9E3779B1u + (uint32_t)seed;
-    h ^= ((uint32_t)(pair >> 32) + (uint32_t)(seed >> 32)) * 0x85EBCA77u;
-    h ^= h >> 16; h *= 0x85EBCA6Bu;
-    h ^= h >> 13; h *= 0xC2B2AE35u;
+// Counter-based RNG for dropout: one 32-bit hash per PAIR of consecutive elements, 15 uniform bits per element
+// (drop probability resolution 2^-15); the backward pass regenerates the mask from the same (seed, index) instead
+// of storing it.  The caller's 64-bit seed is mixed ONCE on the host (splitmix64) into two 32-bit keys; the per-pair hash is
+// two multiply / xor-shift rounds keyed before and between them (6 integer instructions per pair), checked for rate,
+// uniformity and neighbour / cross-seed correlation (all at the 1e-3 sampling-noise level over 4 M pairs).
+__host__ __device__ __forceinline__ uint64_t hd_seed_mix(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// `mixed` = hd_seed_mix(seed); `pair` = (element index >> 1), truncated to 32 bits
+__host__ __device__ __forceinline__ uint32_t hd_hash_pair(uint64_t mixed, uint32_t pair) {
+    uint32_t h = pair * 0x9E3779B1u + (uint32_t)mixed;
     h ^= h >> 16;
+    h = h * 0x85EBCA6Bu + (uint32_t)(mixed >> 32);
+    h ^= h >> 13;
     return h;
 }
-__host__ __device__ __forceinline__ uint32_t hd_dropout_threshold(float p_drop) { return (uint32_t)(p_drop * 65536.f + 0.5f); }
+// element 2j uses bits [0, 15) of the pair's hash, element 2j+1 bits [16, 31); dropped iff field < thr15
+__host__ __device__ __forceinline__ uint32_t hd_dropout_thr15(float p_drop) {
+    uint32_t t = (uint32_t)(p_drop * 32768.f + 0.5f);
+    return t > 0x7FFFu ? 0x7FFFu : t;
+}
 // scale[k] = 0 (dropped) or 1/(1-p) for the V consecutive elements starting at the EVEN element index `base`
 template <int V>
-__host__ __device__ __forceinline__ void hd_dropout_vec(uint64_t seed, uint64_t base, float p_drop, float* scale) {
-    const uint32_t thr = hd_dropout_threshold(p_drop);
+__host__ __device__ __forceinline__ void hd_dropout_vec(uint64_t mixed, uint64_t base, float p_drop, float* scale) {
+    const uint32_t thr = hd_dropout_thr15(p_drop);
     const float keep = 1.f / (1.f - p_drop);
 #pragma unroll
     for (int k = 0; k < V; k += 2) {
-        const uint32_t h = hd_hash_pair(seed, (base >> 1) + (k >> 1));
-        scale[k] = (h & 0xFFFFu) < thr ? 0.f : keep;
-        scale[k + 1] = (h >> 16) < thr ? 0.f : keep;
+        const uint32_t h = hd_hash_pair(mixed, (uint32_t)(base >> 1) + (uint32_t)(k >> 1));
+        scale[k] = (h & 0x7FFFu) < thr ? 0.f : keep;
+        scale[k + 1] = ((h >> 16) & 0x7FFFu) < thr ? 0.f : keep;
     }
 }
+#ifdef __CUDACC__
+// the same decision for a packed bf16 pair: 0xFFFF in every half that is KEPT.  thr2 = thr15 * 0x00010001.
+// ((field | 0x8000) - thr15 keeps bit 15 iff field >= thr15; PRMT replicates the two sign bits over their halves)
+__device__ __forceinline__ uint32_t hd_keep_mask2(uint32_t h, uint32_t thr2) {
+    const uint32_t w = ((h & 0x7FFF7FFFu) | 0x80008000u) - thr2;
+    uint32_t m;      // selector nibbles 9 / B = "replicate the sign of byte 1 / byte 3" (__byte_perm masks that mode bit away)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(w), "r"(0u), "r"(0xBB99u));
+    return m;
+}
+#endif
 
 __device__ __forceinline__ float hd_warp_sum(float v) {
 #pragma unroll

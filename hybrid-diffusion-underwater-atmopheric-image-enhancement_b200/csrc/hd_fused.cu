@@ -8,6 +8,21 @@
 //       (TrainCondition.py:61-63).
 #include "hd_common.cuh"
 
+// second-generation bf16 GroupNorm kernels (hd_gn.cu); the generic templates below serve the fp32 check mode, shapes outside
+// the new kernels' mapping and HDIFF_GN_V1=1
+int hd_gn2_supported(int C0, int C1, int G, int64_t HW, int N);
+int hd_gn2_stats(const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, double* sums, cudaStream_t st);
+int hd_gn2_apply(const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, const double* sums, const float* gamma,
+                 const float* beta, float eps, int act, float p_drop, uint64_t seed, void* out, cudaStream_t st);
+int hd_gn2_bwd_reduce(const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, const double* sums, const float* gamma,
+                      const float* beta, float eps, int act, float p_drop, uint64_t seed, const void* dy, double* gsums,
+                      float* dgamma, float* dbeta, cudaStream_t st);
+int hd_gn2_bwd_apply(const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, const double* sums, const float* gamma,
+                     const float* beta, float eps, int act, float p_drop, uint64_t seed, const void* dy, const double* gsums,
+                     const void* add, const void* acc0, const void* acc1, void* dx0, void* dx1, float* cs_total, float* cs_per_n,
+                     int64_t cs_ld, int cs_n, cudaStream_t st);
+extern "C" int hd_gn_v2(int dtype, int C0, int C1, int G, int64_t HW, int N) { return dtype == HD_BF16 && hd_gn2_supported(C0, C1, G, HW, N); }
+
 template <typename T> struct Vec;
 template <> struct Vec<float> { static constexpr int N = 4; using raw = float4; static constexpr bool fast = false; };
 template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; using raw = uint4; static constexpr bool fast = true; };
@@ -147,6 +162,7 @@ static int gn_stats_t(const void* in0, int C0, const void* in1, int C1, int N, i
 }
 extern "C" int hd_gn_stats(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, double* sums, cudaStream_t stream) {
     HD_REQUIRE(in0 && sums && N > 0 && HW > 0 && C0 > 0 && (C1 == 0 || in1));
+    if (hd_gn_v2(dtype, C0, C1, G, HW, N)) return hd_gn2_stats(in0, C0, in1, C1, N, HW, G, sums, stream);
     if (dtype == HD_F32) return gn_stats_t<float>(in0, C0, in1, C1, N, HW, G, sums, stream);
     if (dtype == HD_BF16) return gn_stats_t<__nv_bfloat16>(in0, C0, in1, C1, N, HW, G, sums, stream);
     return HD_ERR_ARG;
@@ -237,7 +253,8 @@ extern "C" int hd_gn_apply(int dtype, const void* in0, int C0, const void* in1, 
                            const float* gamma, const float* beta, float eps, int act, float p_drop, uint64_t seed, void* out,
                            cudaStream_t stream) {
     HD_REQUIRE(in0 && sums && gamma && beta && out && N > 0 && HW > 0 && (C1 == 0 || in1));
-    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
+    if (hd_gn_v2(dtype, C0, C1, G, HW, N)) return hd_gn2_apply(in0, C0, in1, C1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, out, stream);
+    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, hd_seed_mix(seed)};
     if (dtype == HD_F32) return gn_apply_t<float>(in0, C0, in1, C1, g, out, stream);
     if (dtype == HD_BF16) return gn_apply_t<__nv_bfloat16>(in0, C0, in1, C1, g, out, stream);
     return HD_ERR_ARG;
@@ -343,7 +360,11 @@ extern "C" int hd_gn_bwd_reduce(int dtype, const void* in0, int C0, const void* 
                                 uint64_t seed, const void* dy, double* gsums, float* dgamma, float* dbeta, void* dy_act,
                                 cudaStream_t stream) {
     HD_REQUIRE(in0 && sums && gamma && beta && dy && gsums && dgamma && dbeta && (C1 == 0 || in1));
-    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
+    if (hd_gn_v2(dtype, C0, C1, G, HW, N)) {
+        if (dy_act) { hd_set_error("hd_gn_bwd_reduce: the second-generation kernels do not hand dy' over (ask hd_gn_v2 first)"); return HD_ERR_ARG; }
+        return hd_gn2_bwd_reduce(in0, C0, in1, C1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, dy, gsums, dgamma, dbeta, stream);
+    }
+    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, hd_seed_mix(seed)};
     if (dtype == HD_F32) return gn_bwd_reduce_t<float>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, dy_act, stream);
     if (dtype == HD_BF16) return gn_bwd_reduce_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, dy_act, stream);
     return HD_ERR_ARG;
@@ -534,7 +555,7 @@ extern "C" int hd_gn_bwd_fused(int dtype, const void* in0, int C0, const void* i
                                uint64_t seed, const void* dy, double* gsums, float* dgamma, float* dbeta, const void* add,
                                const void* acc0, const void* acc1, void* dx0, void* dx1, unsigned* counter, cudaStream_t stream) {
     HD_REQUIRE(in0 && sums && gamma && beta && dy && gsums && dgamma && dbeta && dx0 && counter && (C1 == 0 || (in1 && dx1)));
-    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
+    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, hd_seed_mix(seed)};
     if (dtype == HD_F32) return gn_bwd_fused_t<float>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, add, acc0, acc1, dx0, dx1, counter, stream);
     if (dtype == HD_BF16) return gn_bwd_fused_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, dgamma, dbeta, add, acc0, acc1, dx0, dx1, counter, stream);
     return HD_ERR_ARG;
@@ -559,7 +580,12 @@ extern "C" int hd_gn_bwd_apply(int dtype, const void* in0, int C0, const void* i
                                int cs_n, int dy_is_act, cudaStream_t stream) {
     HD_REQUIRE(in0 && sums && gamma && beta && dy && gsums && dx0 && (C1 == 0 || (in1 && dx1)));
     HD_REQUIRE(cs_n >= 0 && cs_n <= C0 + C1);
-    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, seed};
+    if (hd_gn_v2(dtype, C0, C1, G, HW, N)) {
+        if (dy_is_act) { hd_set_error("hd_gn_bwd_apply: the second-generation kernels take the raw dy (ask hd_gn_v2 first)"); return HD_ERR_ARG; }
+        return hd_gn2_bwd_apply(in0, C0, in1, C1, N, HW, G, sums, gamma, beta, eps, act, p_drop, seed, dy, gsums, add, acc0, acc1, dx0, dx1,
+                                cs_total, cs_per_n, cs_ld, cs_n, stream);
+    }
+    GnParams g{N, HW, C0 + C1, G, sums, gamma, beta, eps, act, p_drop, hd_seed_mix(seed)};
     if (dtype == HD_F32) return gn_bwd_apply_t<float>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, cs_total, cs_per_n, cs_ld, cs_n, dy_is_act, stream);
     if (dtype == HD_BF16) return gn_bwd_apply_t<__nv_bfloat16>(in0, C0, in1, C1, g, dy, gsums, add, acc0, acc1, dx0, dx1, cs_total, cs_per_n, cs_ld, cs_n, dy_is_act, stream);
     return HD_ERR_ARG;

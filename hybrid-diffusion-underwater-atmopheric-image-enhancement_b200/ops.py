@@ -152,6 +152,20 @@ class CudaOps:
         self.launches += 3
         self._t1(e0, "attn_bwd_tc" if tc else "attn_bwd_simt", 8.0 * N * S * S * C)
 
+    def mha_fwd(self, qkv, out, lse, N, S, C, heads):
+        """Multi-head self-attention core (nn.MultiheadAttention with q = k = v): qkv [N, S, 3C] -> out [N, S, C], lse [N, heads, S]."""
+        e0 = self._t0()
+        _lib.check(self.lib.hd_mha_fwd(_DT[qkv.dtype], _p(qkv), _p(out), _p(lse), N, S, C, heads, _stream()), "hd_mha_fwd")
+        self.launches += 1
+        self._t1(e0, "mha_fwd", 4.0 * N * S * S * C)
+
+    def mha_bwd(self, qkv, out, dout, lse, delta, dqkv, N, S, C, heads):
+        e0 = self._t0()
+        _lib.check(self.lib.hd_mha_bwd(_DT[qkv.dtype], _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), N, S, C, heads, _stream()),
+                   "hd_mha_bwd")
+        self.launches += 2
+        self._t1(e0, "mha_bwd", 8.0 * N * S * S * C)
+
     # ---- GroupNorm family ----------------------------------------------------------------
     def gn_stats(self, x0, x1, N, HW, G, sums):
         e0 = self._t0()
@@ -191,15 +205,17 @@ class CudaOps:
                                                 _p(self._gn_counter), _stream()), "hd_gn_bwd_fused")
             self.launches += 1
         else:
-            inplace = bool(overwrite_dy) and self.gn_inplace and (act or p_drop > 0)
+            inplace = (bool(overwrite_dy) and self.gn_inplace and (act or p_drop > 0)
+                       and not self.lib.hd_gn_v2(dt, C0, C1, G, HW, N))       # first-generation kernels only (see csrc/hd_gn.cu)
             _lib.check(self.lib.hd_gn_bwd_reduce(*a, _p(gsums), _p(dgamma), _p(dbeta), _p(dy) if inplace else None, _stream()),
                        "hd_gn_bwd_reduce")
             _lib.check(self.lib.hd_gn_bwd_apply(*a, _p(gsums), _p(add), _p(acc0), _p(acc1), _p(dx0), _p(dx1), _p(cs_total), _p(cs_per_n),
                                                 0 if cs_per_n is None else cs_per_n.stride(0),
                                                 (C0 + C1) if cs_n is None else int(cs_n), int(inplace), _stream()), "hd_gn_bwd_apply")
             self.launches += 2
-        nt = 5 + (add is not None) + (acc0 is not None)       # x, dy twice; dx once; optional addends
-        self._t1(e0, "gn_bwd", float(nt * N * HW * (C0 + C1) * x0.element_size()))
+        # compulsory bytes (every operand once): x, dy in, dx out, + the optional addends
+        nb = (3 * (C0 + C1) + (0 if add is None else C0 + C1) + (0 if acc0 is None else C0) + (0 if acc1 is None else C1))
+        self._t1(e0, "gn_bwd", float(nb * N * HW * x0.element_size()))
 
     def colsum(self, t, N, HW, C, per_n, total, nchw=False):
         """per_n[n, c] += sum_pix t ; total[c] += sum_{n,pix} t   (either may be None)."""

@@ -77,10 +77,22 @@ int hd_attn_fwd_wide_tc(const void* qkv, void* out, float* lse, int N, int S, in
 int hd_attn_bwd_wide_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* stats, void* dqkv,
                         int N, int S, int C, hd_stream_t stream);
 
+/* ---- Multi-head self-attention core of the MHA ResBlock: nn.MultiheadAttention(out_ch, 8) on the flattened feature map with
+ *      q = k = v (ModelCondition.py:189,203-208 == diffusion/Model.py:290,304-309; DynamicUNet middle blocks :425-431).
+ *      qkv [N][S][3C] is the packed in-projection's output (q | k | v, head h = channels [h*C/heads, (h+1)*C/heads) of each);
+ *      out / dout [N][S][C]; lse / delta [N][heads][S] fp32 (delta is scratch).  Head dims 4, 8, 16, 32, 64. ---- */
+int hd_mha_supported(int C, int heads);
+int hd_mha_fwd(int dtype, const void* qkv, void* out, float* lse, int N, int S, int C, int heads, hd_stream_t stream);
+int hd_mha_bwd(int dtype, const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+               int N, int S, int C, int heads, hd_stream_t stream);
+
 /* ---- GroupNorm(32) + Swish (+ Dropout): ModelCondition.py:128-129,141-143,95,249-250.  Two-source input
  *      (C0 | C1 channels) fuses torch.cat :271 into the normalisation.  sums/gsums = [N][G][2] fp64. ---- */
 int hd_gn_stats(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, double* sums,
                 hd_stream_t stream);
+/* 1 when the hd_gn_* calls of this shape run on the second-generation bf16 kernels (csrc/hd_gn.cu): those never hand dy' from the
+ * reduce pass to the apply pass (pass dy_act = NULL, dy_is_act = 0) */
+int hd_gn_v2(int dtype, int C0, int C1, int G, int64_t HW, int N);
 /* group statistics [N][G][2] from the per-channel sums of one or two source tensors (see hd_conv_tc chan_sums) */
 int hd_gn_group_sums(const double* cs0, int C0, const double* cs1, int C1, int N, int G, double* sums, hd_stream_t stream);
 int hd_gn_apply(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, const double* sums,

@@ -99,6 +99,24 @@ class EmuOps:
         dqkv.copy_(x.grad.view(dqkv.shape).to(dqkv.dtype))
         self.launches += 3
 
+    def mha_fwd(self, qkv, out, lse, N, S, C, heads):
+        hd = C // heads
+        q, kk, v = (t.reshape(N, S, heads, hd).permute(0, 2, 1, 3) for t in qkv.float().view(N, S, 3, C).unbind(2))
+        s = torch.matmul(q, kk.transpose(-1, -2)) * (hd ** -0.5)
+        lse.copy_(torch.logsumexp(s, dim=-1))
+        out.copy_(torch.matmul(torch.softmax(s, -1), v).permute(0, 2, 1, 3).reshape(out.shape).to(out.dtype))
+        self.launches += 1
+
+    def mha_bwd(self, qkv, out, dout, lse, delta, dqkv, N, S, C, heads):
+        hd = C // heads
+        x = qkv.float().view(N, S, 3, C).clone().requires_grad_(True)
+        with torch.enable_grad():
+            q, kk, v = (t.reshape(N, S, heads, hd).permute(0, 2, 1, 3) for t in x.unbind(2))
+            o = torch.matmul(torch.softmax(torch.matmul(q, kk.transpose(-1, -2)) * (hd ** -0.5), -1), v).permute(0, 2, 1, 3).reshape(N, S, C)
+            o.backward(dout.float().view(N, S, C))
+        dqkv.copy_(x.grad.view(dqkv.shape).to(dqkv.dtype))
+        self.launches += 2
+
     # ---- GroupNorm family ----
     @staticmethod
     def _cat(x0, x1):

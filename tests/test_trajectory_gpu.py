@@ -162,14 +162,16 @@ def test_fixed_noise_1000_step_cfg_sampling_psnr_on_a_trained_network():
     # ---- train the ORACLE for a few hundred steps on smooth synthetic images (class = colour cast), copy the weights ----
     ref.train()
     rtr = R.GaussianDiffusionTrainer(ref, 1e-4, 0.02, 1000).to(dev)
-    ropt = torch.optim.AdamW(ref.parameters(), lr=2e-4, weight_decay=1e-4)
+    # recipe found with scripts/explore_saturation.py: 400 steps on +-0.9 images leave 73 % of the sampled pixels clipped,
+    # 1500 steps at lr 3e-4 on +-0.5 images leave 33 %
+    ropt = torch.optim.AdamW(ref.parameters(), lr=3e-4, weight_decay=1e-4)
     g = torch.Generator(device="cuda").manual_seed(5)
     yy, xx = torch.meshgrid(torch.linspace(-1, 1, res, device=dev), torch.linspace(-1, 1, res, device=dev), indexing="ij")
-    for s in range(int(os.environ.get("HDIFF_TRAJ_PRETRAIN", "400"))):
+    for s in range(int(os.environ.get("HDIFF_TRAJ_PRETRAIN", "1500"))):
         lab = torch.randint(0, 10, (16,), generator=g, device=dev) + 1
         ph = torch.rand(16, 3, 1, 1, generator=g, device=dev) * 6.28
         fr = 1 + 3 * torch.rand(16, 3, 1, 1, generator=g, device=dev)
-        x = 0.6 * torch.sin(fr * xx + ph) * torch.cos(fr * yy - ph) + 0.3 * ((lab.view(-1, 1, 1, 1).float() - 5.5) / 5.5)
+        x = 0.35 * torch.sin(fr * xx + ph) * torch.cos(fr * yy - ph) + 0.15 * ((lab.view(-1, 1, 1, 1).float() - 5.5) / 5.5)
         if s % 10 == 0:
             lab = torch.zeros_like(lab)                               # label dropout (TrainCondition.py:57-58)
         R.train_step(rtr, ropt, x.clamp(-1, 1), lab)
