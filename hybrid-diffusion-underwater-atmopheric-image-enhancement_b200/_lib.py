@@ -52,6 +52,9 @@ PROTOTYPES = {
     "hd_attn_fwd_wide_tc": [P, P, P, I, I, I, P],
     "hd_attn_bwd_wide_tc": [P, P, P, P, P, P, I, I, I, P],
     "hd_attn_bwd_tc_supported": [I, I],
+    "hd_upsample_nearest": [I, P, P, I, I, I, I, I, I, P],
+    "hd_upsample_nearest_bwd": [I, P, P, I, I, I, I, I, I, P],
+    "hd_image_affine": [P, I, P, F, F, L, P],
     "hd_mha_supported": [I, I],
     "hd_mha_fwd": [I, P, P, P, I, I, I, I, P],
     "hd_mha_bwd": [I, P, P, P, P, P, P, I, I, I, I, P],

@@ -628,6 +628,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* t, int N, int64_t 
         if (total) atomicAdd(total + i, s_col[i]);
     }
 }
+// any channel count (the 4 / 8-channel maps of the image condition encoder): thread <-> element, shared partials per block
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_generic_kernel(const T* t, int64_t HW, int C, int64_t pix_per_block, float* per_n, int64_t ld, float* total) {
+    extern __shared__ float s_col[];
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_col[i] = 0.f;
+    __syncthreads();
+    const int64_t p0 = blockIdx.x * pix_per_block, p1 = p0 + pix_per_block < HW ? p0 + pix_per_block : HW;
+    const T* base = t + (int64_t)n * HW * C;
+    for (int64_t e = p0 * C + threadIdx.x; e < p1 * C; e += blockDim.x) atomicAdd(&s_col[e % C], hd_ld(base + e));
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        if (per_n) atomicAdd(per_n + (int64_t)n * ld + i, s_col[i]);
+        if (total) atomicAdd(total + i, s_col[i]);
+    }
+}
 __global__ void colsum_nchw_kernel(const float* t, int C, int64_t HW, float* per_n, int64_t ld, float* total) {
     // block per (n, c)
     __shared__ float red[8];
@@ -654,6 +670,13 @@ extern "C" int hd_colsum(int dtype, const void* t, int nchw_f32, int N, int64_t 
         return HD_OK;
     }
     int V = dtype == HD_F32 ? 4 : 8;
+    if (C % V != 0 && C <= 4096 && (dtype == HD_F32 || dtype == HD_BF16)) {
+        int chunks; const int64_t ppb = pick_chunk(N, HW, 64, &chunks);
+        if (dtype == HD_F32) colsum_generic_kernel<float><<<dim3(chunks, N), 256, C * sizeof(float), stream>>>((const float*)t, HW, C, ppb, per_n, ld_per_n, total);
+        else colsum_generic_kernel<__nv_bfloat16><<<dim3(chunks, N), 256, C * sizeof(float), stream>>>((const __nv_bfloat16*)t, HW, C, ppb, per_n, ld_per_n, total);
+        HD_CHECK_LAUNCH();
+        return HD_OK;
+    }
     if (C % V != 0 || C / V > 256) { hd_set_error("colsum: unsupported channel count"); return HD_ERR_UNSUPPORTED; }
     int ppi = 256 / (C / V), chunks;
     int64_t ppb = pick_chunk(N, HW, ppi, &chunks);

@@ -37,7 +37,12 @@ struct ConvArgs {
 
 template <typename T>
 __device__ __forceinline__ float conv_in_load(const ConvArgs<T>& a, int n, int y, int x, int j) {
-    if (a.in_nchw) return a.in_nchw[(((int64_t)n * a.C0 + j) * a.H + y) * a.W + x];
+    if (a.in_nchw) {
+        if (a.P_in == 1) return a.in_nchw[(((int64_t)n * a.C0 + j) * a.H + y) * a.W + x];
+        // 2x2 space-to-depth view of an NCHW image (stride-2 convolutions of the image condition encoder, diffusion/Model.py:119-121)
+        const int q = j / a.C0, c = j - q * a.C0;
+        return a.in_nchw[(((int64_t)n * a.C0 + c) * (2 * a.H) + (2 * y + (q >> 1))) * (2 * a.W) + (2 * x + (q & 1))];
+    }
     if (a.P_in == 1) {
         if (j < a.C0) return hd_ld(a.in0 + ((((int64_t)n * a.H + y) * a.W + x) * a.C0 + j));
         return hd_ld(a.in1 + ((((int64_t)n * a.H + y) * a.W + x) * a.C1 + (j - a.C0)));
@@ -83,7 +88,7 @@ extern "C" int hd_conv_simt(int dtype, const void* in0, int C0, const void* in1,
                             int N, int H, int W, int ksize, cudaStream_t stream) {
     HD_REQUIRE(in0 && w && out);
     HD_REQUIRE(ksize == 1 || ksize == 3);
-    HD_REQUIRE(P_in == 1 || (P_in == 2 && C1 == 0 && !in_nchw_f32));
+    HD_REQUIRE(P_in == 1 || (P_in == 2 && C1 == 0));
     HD_REQUIRE(P_out == 1 || (P_out == 2 && !out_nchw_f32 && !emb));
     HD_REQUIRE(N > 0 && H > 0 && W > 0 && C0 > 0 && Cout > 0 && out_nchw_f32 >= 0 && out_nchw_f32 <= Cout);
     int64_t total = (int64_t)N * H * W * Cout * P_out * P_out;
@@ -148,7 +153,7 @@ extern "C" int hd_wgrad_simt(int dtype, const void* in0, int C0, const void* in1
                              int N, int H, int W, int ksize, cudaStream_t stream) {
     HD_REQUIRE(in0 && dy && dw);
     HD_REQUIRE(ksize == 1 || ksize == 3);
-    HD_REQUIRE(P_in == 1 || (P_in == 2 && C1 == 0 && !in_nchw_f32));
+    HD_REQUIRE(P_in == 1 || (P_in == 2 && C1 == 0));
     HD_REQUIRE(P_dy == 1 || (P_dy == 2 && !dy_nchw_f32));
     const int CoutL = Cdy * P_dy * P_dy, CinL = (C0 + C1) * P_in * P_in;
     const int64_t npix = (int64_t)N * H * W;

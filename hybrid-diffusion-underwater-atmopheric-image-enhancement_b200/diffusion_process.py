@@ -143,6 +143,10 @@ class GaussianDiffusionSampler(nn.Module):
         assert x_t.shape == eps.shape
         return extract(self.coeff1, t, x_t.shape) * x_t - extract(self.coeff2, t, x_t.shape) * eps
 
+    def _eval_model(self, x, t):
+        """the unconditional network evaluation of one step (the hybrid sampler prepends its conditioning image here)"""
+        return self.model(x, t)
+
     def _eps_pair(self, x, t, labels):
         """(eps_cond, eps_uncond) — batched as 2B when the model accepts it."""
         B = x.shape[0]
@@ -161,7 +165,7 @@ class GaussianDiffusionSampler(nn.Module):
         B = x.shape[0]
         t = (step.to(torch.int64) * stride).expand(B).contiguous()
         if labels is None:
-            eps_c, eps_u = self.model(x, t), None
+            eps_c, eps_u = self._eval_model(x, t), None
         else:
             eps_c, eps_u = self._eps_pair(x, t, labels)
             eps_u = eps_u.contiguous()

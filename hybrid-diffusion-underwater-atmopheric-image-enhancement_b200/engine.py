@@ -72,6 +72,22 @@ class ConditionalEmbedding(nn.Module):
             nn.Linear(d_model, dim), Swish(), nn.Linear(dim, dim))
 
 
+class ImageConditionalEmbedding(nn.Module):
+    """DynamicUNet's condition encoder (diffusion/Model.py:110-167): three stride-2 3x3 convolutions (no activation between
+    them), global average pool, Linear -> Swish -> Linear.  Parameter container; the engine runs it."""
+
+    def __init__(self, d_model, dim):
+        super().__init__()
+        channels = d_model // 16
+        self.conv1 = nn.Conv2d(3, channels, kernel_size=3, stride=2, padding=1)
+        self.conv2 = nn.Conv2d(channels, channels * 2, kernel_size=3, stride=2, padding=1)
+        self.conv3 = nn.Conv2d(channels * 2, channels * 4, kernel_size=3, stride=2, padding=1)
+        self.pool = nn.AdaptiveAvgPool2d((1, 1))
+        self.linear1 = nn.Linear(channels * 4, dim)
+        self.activation = Swish()
+        self.linear2 = nn.Linear(dim, dim)
+
+
 class DownSample(nn.Module):
     def __init__(self, in_ch):
         super().__init__()
@@ -96,17 +112,31 @@ class AttnBlock(nn.Module):
         self.proj = nn.Conv2d(in_ch, in_ch, 1)
 
 
+MHA_HEADS = 8      # nn.MultiheadAttention(out_ch, num_heads=8), ModelCondition.py:189 == diffusion/Model.py:290
+
+
 class ResBlock(nn.Module):
-    def __init__(self, in_ch, out_ch, tdim, dropout, attn=False):
+    """attn=True, mha=False: ResBlock_old + AttnBlock (GroupNorm, single head, residual; ModelCondition.py:124-164).
+    attn=True, mha=True: the reference's live ResBlock (ModelCondition.py:166-211 == diffusion/Model.py:267-312): 8-head
+    nn.MultiheadAttention on the flattened map whose output REPLACES h (no norm, no residual)."""
+
+    def __init__(self, in_ch, out_ch, tdim, dropout, attn=False, mha=False):
         super().__init__()
         self.in_ch, self.out_ch, self.p_drop = in_ch, out_ch, float(dropout)
+        self.mha = bool(attn and mha)
         self.block1 = nn.Sequential(nn.GroupNorm(32, in_ch), Swish(), nn.Conv2d(in_ch, out_ch, 3, stride=1, padding=1))
         self.temb_proj = nn.Sequential(Swish(), nn.Linear(tdim, out_ch))
         self.cond_proj = nn.Sequential(Swish(), nn.Linear(tdim, out_ch))
         self.block2 = nn.Sequential(nn.GroupNorm(32, out_ch), Swish(), nn.Dropout(dropout),
                                     nn.Conv2d(out_ch, out_ch, 3, stride=1, padding=1))
-        self.shortcut = nn.Conv2d(in_ch, out_ch, 1) if in_ch != out_ch else nn.Identity()
-        self.attn = AttnBlock(out_ch) if attn else nn.Identity()
+        # registration order = state_dict key order: ResBlock_old has shortcut before attn (ModelCondition.py:145-153), the MHA
+        # ResBlock attn before shortcut (:189-194)
+        if attn and mha:
+            self.attn = nn.MultiheadAttention(out_ch, num_heads=MHA_HEADS)       # holds in_proj_weight / in_proj_bias / out_proj.*
+            self.shortcut = nn.Conv2d(in_ch, out_ch, 1) if in_ch != out_ch else nn.Identity()
+        else:
+            self.shortcut = nn.Conv2d(in_ch, out_ch, 1) if in_ch != out_ch else nn.Identity()
+            self.attn = AttnBlock(out_ch) if attn else nn.Identity()
 
 
 # =============================================================================================
@@ -152,6 +182,24 @@ def _tbl_down(off3, off5, C):
     return A.view(C, 3, 3, 4 * C), B.view(C, 3, 3, 4 * C)
 
 
+def _tbl_s2(off3, Co, Ci):
+    """Conv2d(Ci, Co, 3, stride=2, padding=1) as a 3x3 stride-1 convolution over the 2x2 space-to-depth view:
+    W'[co][ty][tx][(py, px, ci)] = W[co][ci][2(ty-1)+py+1][2(tx-1)+px+1] (taps outside the 3x3 kernel stay zero)."""
+    i3 = torch.arange(Co * Ci * 9, dtype=torch.int64).view(Co, Ci, 3, 3) + off3
+    A = torch.full((Co, 3, 3, 2, 2, Ci), -1, dtype=torch.int64)
+    for ty in range(3):
+        for py in range(2):
+            dy = 2 * (ty - 1) + py + 1
+            if not 0 <= dy <= 2:
+                continue
+            for tx in range(3):
+                for px in range(2):
+                    dx = 2 * (tx - 1) + px + 1
+                    if 0 <= dx <= 2:
+                        A[:, ty, tx, py, px, :] = i3[:, :, dy, dx]
+    return A.view(Co, 3, 3, 4 * Ci)
+
+
 def _tbl_convT(off, C):
     """ConvTranspose2d(C, C, 5, 2, 2, 1) (ModelCondition.py:83): out[2Y+py, 2X+px, co] is a 3x3 stride-1
     convolution of the input with W''[(py,px,co)][ty][tx][ci] = Wt[ci][co][2(1-ty)+py+2][2(1-tx)+px+2]."""
@@ -182,46 +230,56 @@ class UNetBase(nn.Module):
     kernels.  `attn` lists the levels whose down-path ResBlocks carry an AttnBlock (SURVEY.md F1/F4);
     the middle is [attn, no-attn], the up path has none (ModelCondition.py:233-236,242)."""
 
-    def __init__(self, T, ch, ch_mult, attn, num_res_blocks, dropout, num_labels=None, compute_dtype=None):
+    def __init__(self, T, ch, ch_mult, attn, num_res_blocks, dropout, num_labels=None, compute_dtype=None, mha=False,
+                 in_channels=3, middle_attn=(True, False), up_extra=1, image_cond=False):
+        """mha: attention ResBlocks are the reference's live nn.MultiheadAttention variant (ModelCondition.py:166-211).
+        attn: levels whose down-path ResBlocks carry attention ("all": every level, as the live UNet :226 builds them).
+        in_channels / middle_attn / up_extra / image_cond describe DynamicUNet (diffusion/Model.py:382-517): 6-channel head,
+        four attention middle blocks, num_res_blocks (not + 1) up blocks per level, image condition encoder."""
         super().__init__()
+        attn = list(range(len(ch_mult))) if attn == "all" else list(attn)
         assert all(i < len(ch_mult) for i in attn), 'attn index out of bound'
         if compute_dtype is None:
             compute_dtype = torch.float32 if os.environ.get("HDIFF_COMPUTE", "bf16") == "fp32" else torch.bfloat16
         assert compute_dtype in (torch.float32, torch.bfloat16)
         self.compute_dtype = compute_dtype
         self.T, self.ch, self.num_labels = T, ch, num_labels
+        self.mha, self.in_channels, self.image_cond, self.up_extra = bool(mha), int(in_channels), bool(image_cond), int(up_extra)
+        assert 1 <= self.in_channels <= 8
         tdim = ch * 4
         self.tdim = tdim
         self.time_embedding = TimeEmbedding(T, ch, tdim)
-        if num_labels is not None:
+        if image_cond:
+            assert ch % 32 == 0
+            self.cond_embedding = ImageConditionalEmbedding(ch, tdim)
+        elif num_labels is not None:
             self.cond_embedding = ConditionalEmbedding(num_labels, ch, tdim)
-        self.head = nn.Conv2d(3, ch, kernel_size=3, stride=1, padding=1)
+        self.head = nn.Conv2d(self.in_channels, ch, kernel_size=3, stride=1, padding=1)
         self.downblocks = nn.ModuleList()
         chs = [ch]
         now_ch = ch
         for i, mult in enumerate(ch_mult):
             out_ch = ch * mult
             for _ in range(num_res_blocks):
-                self.downblocks.append(ResBlock(now_ch, out_ch, tdim, dropout, attn=(i in attn)))
+                self.downblocks.append(ResBlock(now_ch, out_ch, tdim, dropout, attn=(i in attn), mha=mha))
                 now_ch = out_ch
                 chs.append(now_ch)
             if i != len(ch_mult) - 1:
                 self.downblocks.append(DownSample(now_ch))
                 chs.append(now_ch)
-        self.middleblocks = nn.ModuleList([ResBlock(now_ch, now_ch, tdim, dropout, attn=True),
-                                           ResBlock(now_ch, now_ch, tdim, dropout, attn=False)])
+        self.middleblocks = nn.ModuleList([ResBlock(now_ch, now_ch, tdim, dropout, attn=bool(a), mha=mha) for a in middle_attn])
         self.upblocks = nn.ModuleList()
         self._up_split = []      # per up ResBlock: (C0 from below, C1 from the skip)
         for i, mult in reversed(list(enumerate(ch_mult))):
             out_ch = ch * mult
-            for _ in range(num_res_blocks + 1):
+            for _ in range(num_res_blocks + up_extra):
                 skip = chs.pop()
                 self.upblocks.append(ResBlock(skip + now_ch, out_ch, tdim, dropout, attn=False))
                 self._up_split.append((now_ch, skip))
                 now_ch = out_ch
             if i != 0:
                 self.upblocks.append(UpSample(now_ch))
-        assert len(chs) == 0
+        assert up_extra != 1 or len(chs) == 0
         self.tail = nn.Sequential(nn.GroupNorm(32, now_ch), Swish(), nn.Conv2d(now_ch, 3, 3, stride=1, padding=1))
         self._state = None       # built lazily on the parameters' device
         self._frozen = False
@@ -256,7 +314,8 @@ class UNetBase(nn.Module):
         seen = {id(p) for p in order}
         # convolution parameters last: their gradients are produced in packed form (gpk) and all-reduced there, so
         # the data-parallel exchange of the flat buffer only covers the prefix [0, n_direct)
-        conv_ids = {id(p) for m in self.modules() if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)) for p in m.parameters()}
+        conv_ids = {id(p) for m in self.modules() if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.MultiheadAttention))
+                    for p in m.parameters()}
         order += [p for p in named.values() if id(p) not in seen and id(p) not in conv_ids]
         n_direct_params = len(order)
         order += [p for p in named.values() if id(p) not in seen and id(p) in conv_ids]
@@ -337,6 +396,24 @@ class UNetBase(nn.Module):
             bidx[:Co] = torch.arange(Co, dtype=torch.int64) + O(m.bias)
             return add(s, tbl, bias_a=bidx, bias_inv=[(O(m.bias), Co)])
 
+        def linear_spec(name, w, bvec):
+            """a Linear / packed projection [Co, Ci] run as a 1x1 convolution (its weight IS the packed GEMM layout)"""
+            Co, Ci = w.shape
+            return add(ConvSpec(name, 1, Ci, Co, 1, 1), _tbl_conv(O(w), Co, Ci, 1),
+                       bias_a=torch.arange(Co, dtype=torch.int64) + O(bvec), bias_inv=[(O(bvec), Co)])
+
+        # the image condition encoder's stride-2 convolutions come FIRST in the packed buffers: their gradients are the last
+        # ones of a backward pass, and the data-parallel exchange walks the buffer from its end
+        st.cond = {}
+        if self.image_cond:
+            ce = self.cond_embedding
+            for nm in ("conv1", "conv2", "conv3"):
+                m = getattr(ce, nm)
+                Co, Ci = m.weight.shape[:2]
+                sp_ = ConvSpec("cond_" + nm, 3, Ci, Co, 2, 1)
+                sp_.alg_frac = 9.0 / 36.0
+                st.cond[nm] = add(sp_, _tbl_s2(O(m.weight), Co, Ci), bias_a=torch.arange(Co, dtype=torch.int64) + O(m.bias),
+                                  bias_inv=[(O(m.bias), Co)])
         st.pad_io = self.compute_dtype == torch.bfloat16
         st.head = conv_spec("head", self.head, pad_in=64 if st.pad_io else None)
         st.tail = conv_spec("tail", self.tail[2], pad_out=64 if st.pad_io else None)
@@ -349,7 +426,10 @@ class UNetBase(nn.Module):
                 b["conv2"] = conv_spec("conv2", mod.block2[3])
                 if isinstance(mod.shortcut, nn.Conv2d):
                     b["shortcut"] = conv_spec("shortcut", mod.shortcut)
-                if isinstance(mod.attn, AttnBlock):
+                if mod.mha:
+                    b["qkv"] = linear_spec("qkv", mod.attn.in_proj_weight, mod.attn.in_proj_bias)
+                    b["proj"] = linear_spec("proj", mod.attn.out_proj.weight, mod.attn.out_proj.bias)
+                elif isinstance(mod.attn, AttnBlock):
                     a = mod.attn
                     C = mod.out_ch
                     s = ConvSpec("qkv", 1, C, 3 * C, 1, 1)
@@ -456,14 +536,15 @@ class UNetBase(nn.Module):
         st.chan_off += n
         return v
 
-    def _conv(self, st, spec, x0, x1=None, emb=None, res=None, dgrad=False, in_nchw=False, out_nchw=False, want_stats=False):
+    def _conv(self, st, spec, x0, x1=None, emb=None, res=None, dgrad=False, in_nchw=False, out_nchw=False, want_stats=False,
+              quiet=False):
         """want_stats: let the kernel's epilogue leave per-image per-channel (sum, sum of squares) of the output for the
         GroupNorm that reads it next (tcgen05 path only; otherwise _gn_fwd falls back to the statistics kernel)."""
         ops = _ops.get()
         P_in, P_out = (spec.P_out, spec.P_in) if dgrad else (spec.P_in, spec.P_out)
         Cout = spec.Cin if dgrad else spec.Cout
         if in_nchw:
-            N, _, H, W = x0.shape
+            N, H, W = x0.shape[0], x0.shape[2] // P_in, x0.shape[3] // P_in
         else:
             N, H, W = x0.shape[0], x0.shape[1] // P_in, x0.shape[2] // P_in
         if out_nchw:
@@ -478,17 +559,17 @@ class UNetBase(nn.Module):
                 cs = self._chan_alloc(st, N, Cout)
         got = ops.conv(x0, x1, P_in, self._wv(st, spec, dgrad), None if dgrad else self._bv(st, spec), emb, res, out, P_out,
                        N, H, W, spec.k, in_nchw=in_nchw, out_nchw=out_nchw, alg_frac=spec.alg_frac,
-                       Cout_pad=Cout if out_nchw and Cout != spec.real_cout else None, chan_sums=cs)
+                       Cout_pad=Cout if out_nchw and Cout != spec.real_cout else None, chan_sums=cs, quiet=quiet)
         if cs is not None and got:
             st.chan[id(out)] = (weakref.ref(out), cs)     # keyed by the tensor OBJECT: an address can be reused after a free
         return out
 
-    def _wgrad(self, st, spec, x0, x1, dy, in_nchw=False, dy_nchw=False, bias_done=False):
+    def _wgrad(self, st, spec, x0, x1, dy, in_nchw=False, dy_nchw=False, bias_done=False, quiet=False):
         """weight gradient into gpk (packed layout) + bias gradient (column sums of dy; `bias_done`: the producer of dy
         already accumulated them, see _gn_bwd)."""
         ops = _ops.get()
         if in_nchw:
-            N, _, H, W = x0.shape
+            N, H, W = x0.shape[0], x0.shape[2] // spec.P_in, x0.shape[3] // spec.P_in
         else:
             N, H, W = x0.shape[0], x0.shape[1] // spec.P_in, x0.shape[2] // spec.P_in
         dw = st.gpk[spec.w_off // 2: spec.w_off // 2 + spec.n_w]
@@ -500,7 +581,7 @@ class UNetBase(nn.Module):
                     t.record_stream(side)                     # the allocator must not hand the block out while `side` reads it
         with torch.cuda.stream(side) if side is not None else _nullctx():
             ops.wgrad(x0, x1, spec.P_in, dy, spec.P_out, dw, N, H, W, spec.k, self.compute_dtype, in_nchw=in_nchw, dy_nchw=dy_nchw,
-                      alg_frac=spec.alg_frac)
+                      alg_frac=spec.alg_frac, quiet=quiet)
             if spec.has_bias and not bias_done and id(spec) not in st.bias_done:
                 C = spec.Cout                       # physical channels of dy (bias is per physical channel)
                 db = st.gpk[st.n_dw + spec.b_off: st.n_dw + spec.b_off + C]
@@ -578,7 +659,19 @@ class UNetBase(nn.Module):
             s = x0
         h2 = self._conv(st, sp["conv2"], a2, res=s, want_stats=True)
         out = h2
-        if "qkv" in sp:
+        if rb.mha:
+            # nn.MultiheadAttention(q = k = v = h): packed in-projection, 8 heads, out-projection; the result REPLACES h
+            # (no norm, no residual: ModelCondition.py:203-208)
+            ops = _ops.get()
+            N, H, W, C = h2.shape
+            qkv = self._conv(st, sp["qkv"], h2)
+            o = torch.empty_like(h2)
+            lse = torch.empty((N, MHA_HEADS, H * W), dtype=torch.float32, device=h2.device)
+            ops.mha_fwd(qkv, o, lse, N, H * W, C, MHA_HEADS)
+            out = self._conv(st, sp["proj"], o, want_stats=True)
+            if save:
+                ctx.update(qkv=qkv, o=o, lse=lse)
+        elif "qkv" in sp:
             ops = _ops.get()
             N, H, W, C = h2.shape
             g, sums3 = self._gn_fwd(h2, None, rb.attn.group_norm, act=0)
@@ -608,7 +701,16 @@ class UNetBase(nn.Module):
         ops = _ops.get()
         sp = st.blocks[id(rb)]
         x0, x1 = ctx["x0"], ctx["x1"]
-        if "qkv" in sp:
+        if rb.mha:
+            N, H, W, C = ctx["h2"].shape
+            self._wgrad(st, sp["proj"], ctx["o"], None, d_out)
+            d_o = self._conv(st, sp["proj"], d_out, dgrad=True)
+            dqkv = torch.empty_like(ctx["qkv"])
+            delta = torch.empty((N, MHA_HEADS, H * W), dtype=torch.float32, device=d_out.device)
+            ops.mha_bwd(ctx["qkv"], ctx["o"], d_o, ctx["lse"], delta, dqkv, N, H * W, C, MHA_HEADS)
+            self._wgrad(st, sp["qkv"], ctx["h2"], None, dqkv)
+            d_h2 = self._conv(st, sp["qkv"], dqkv, dgrad=True)
+        elif "qkv" in sp:
             N, H, W, C = ctx["h2"].shape
             self._wgrad(st, sp["proj"], ctx["o"], None, d_out)
             d_o = self._conv(st, sp["proj"], d_out, dgrad=True)
@@ -642,7 +744,39 @@ class UNetBase(nn.Module):
         return self._gn_bwd(st, x0, x1, rb.block1[0], ctx["sums1"], 1, 0.0, 0, d_a1, add=add, acc0=acc0, cs_total=cs,
                             cs_n=x0.shape[-1])
 
-    def _run_forward(self, x, t, labels, save):
+    def _cond_fwd(self, st, labels, ctx, save):
+        """Image condition encoder (diffusion/Model.py:153-167): conv s2 x3 (CUDA-core kernels: 4..16 channels), global average
+        pool, Linear.  Returns c0 [N, 4 * channels] fp32 (the pooled features, input of linear1)."""
+        ops = _ops.get()
+        sp = st.cond
+        lab = labels.contiguous().float()
+        N = lab.shape[0]
+        y1 = self._conv(st, sp["conv1"], lab, in_nchw=True, quiet=True)
+        y2 = self._conv(st, sp["conv2"], y1, quiet=True)
+        y3 = self._conv(st, sp["conv3"], y2, quiet=True)
+        C3, HW3 = y3.shape[-1], y3.shape[1] * y3.shape[2]
+        c0 = torch.zeros((N, C3), dtype=torch.float32, device=lab.device)
+        ops.colsum(y3, N, HW3, C3, c0, None)
+        c0.mul_(1.0 / HW3)
+        if save:
+            ctx.update(cond_lab=lab, cond_y1=y1, cond_y2=y2, cond_shape3=tuple(y3.shape))
+        return c0
+
+    def _cond_bwd(self, st, ctx, d_c0):
+        """backward of _cond_fwd from the gradient of the pooled features"""
+        ops = _ops.get()
+        sp = st.cond
+        N, H3, W3, C3 = ctx["cond_shape3"]
+        d_pool = (d_c0 * (1.0 / (H3 * W3))).to(self.compute_dtype).view(N, 1, 1, C3).contiguous()
+        d_y3 = torch.empty((N, H3, W3, C3), dtype=self.compute_dtype, device=d_c0.device)
+        ops.upsample_nearest(d_pool, d_y3)                                   # mean-pool backward: every pixel gets d / (H W)
+        self._wgrad(st, sp["conv3"], ctx["cond_y2"], None, d_y3, quiet=True)
+        d_y2 = self._conv(st, sp["conv3"], d_y3, dgrad=True, quiet=True)
+        self._wgrad(st, sp["conv2"], ctx["cond_y1"], None, d_y2, quiet=True)
+        d_y1 = self._conv(st, sp["conv2"], d_y2, dgrad=True, quiet=True)
+        self._wgrad(st, sp["conv1"], ctx["cond_lab"], None, d_y1, in_nchw=True, quiet=True)
+
+    def _run_forward(self, x, t, labels, save, context_zero=False):
         ops = _ops.get()
         st = self._get_state()
         if not self._frozen:
@@ -650,7 +784,7 @@ class UNetBase(nn.Module):
         training = self.training
         dev = x.device
         st.chan, st.chan_pool, st.chan_off = {}, None, 0
-        assert x.dim() == 4 and x.shape[1] == 3 and x.dtype == torch.float32
+        assert x.dim() == 4 and x.shape[1] == self.in_channels and x.dtype == torch.float32
         x = x.contiguous()
         N = x.shape[0]
         t = t.to(torch.int64).contiguous()
@@ -671,17 +805,28 @@ class UNetBase(nn.Module):
         b_t = st.flat[st.o_tb: st.o_tb + st.emb_total]
         ops.linear_fwd(temb, w_t, b_t, emb_all, in_swish=True)
         ctx.update(t=t, e0=e0, e1=e1, temb=temb)
-        if labels is not None:
-            labels = labels.to(torch.int64).contiguous()
-            ce = self.cond_embedding.condEmbedding
-            c0 = torch.empty((N, self.ch), **f32)
-            ops.embedding_fwd(ce[0].weight, labels, c0)
+        w_c = st.flat[st.o_cw: st.o_cw + st.emb_total * self.tdim].view(st.emb_total, self.tdim)
+        b_c = st.flat[st.o_cb: st.o_cb + st.emb_total]
+        if self.image_cond and (context_zero or labels is None):
+            # DynamicUNet with context_zero (diffusion/Model.py:483-484): cemb = 0, so cond_proj adds its bias only
+            cemb = torch.zeros((N, self.tdim), **f32)
+            ops.linear_fwd(cemb, w_c, b_c, emb_all, in_swish=True, accumulate=True)
+            ctx.update(cemb=cemb, cond_zero=True)
+        elif labels is not None:
+            if self.image_cond:
+                ce = self.cond_embedding
+                lin1, lin2 = ce.linear1, ce.linear2
+                c0 = self._cond_fwd(st, labels, ctx, save)
+            else:
+                labels = labels.to(torch.int64).contiguous()
+                ce = self.cond_embedding.condEmbedding
+                lin1, lin2 = ce[1], ce[3]
+                c0 = torch.empty((N, self.ch), **f32)
+                ops.embedding_fwd(ce[0].weight, labels, c0)
             c1 = torch.empty((N, self.tdim), **f32)
-            ops.linear_fwd(c0, ce[1].weight, ce[1].bias, c1)
+            ops.linear_fwd(c0, lin1.weight, lin1.bias, c1)
             cemb = torch.empty((N, self.tdim), **f32)
-            ops.linear_fwd(c1, ce[3].weight, ce[3].bias, cemb, in_swish=True)
-            w_c = st.flat[st.o_cw: st.o_cw + st.emb_total * self.tdim].view(st.emb_total, self.tdim)
-            b_c = st.flat[st.o_cb: st.o_cb + st.emb_total]
+            ops.linear_fwd(c1, lin2.weight, lin2.bias, cemb, in_swish=True)
             ops.linear_fwd(cemb, w_c, b_c, emb_all, in_swish=True, accumulate=True)
             ctx.update(labels=labels, c0=c0, c1=c1, cemb=cemb)
         # ---- head ----
@@ -711,9 +856,23 @@ class UNetBase(nn.Module):
             h, c = self._res_fwd(st, mod, ri, h, None, emb_all, save, training)
             ri += 1
             bctx.append(c)
+        n_skips = len(hs)
         for mod in self.upblocks:
             if isinstance(mod, ResBlock):
-                h, c = self._res_fwd(st, mod, ri, h, hs.pop(), emb_all, save, training)
+                sk = hs.pop()
+                sk_idx = len(hs)                       # position of this skip in the list the down path built
+                if sk.shape[1:3] != h.shape[1:3]:
+                    # DynamicUNet pops fewer skips than it pushed, so a skip can be one level coarser than h:
+                    # F.interpolate(skip_h, size=h.shape[2:], mode="nearest") (diffusion/Model.py:506-510)
+                    assert h.shape[1] % sk.shape[1] == 0 and h.shape[2] % sk.shape[2] == 0, "nearest skip resize: integer factors only"
+                    up = torch.empty((N, h.shape[1], h.shape[2], sk.shape[3]), dtype=sk.dtype, device=dev)
+                    ops.upsample_nearest(sk, up)
+                    small_shape, sk = tuple(sk.shape), up
+                else:
+                    small_shape = None
+                h, c = self._res_fwd(st, mod, ri, h, sk, emb_all, save, training)
+                if save:
+                    c["skip_idx"], c["skip_small"] = sk_idx, small_shape
                 ri += 1
             else:
                 sp = st.blocks[id(mod)]
@@ -722,7 +881,8 @@ class UNetBase(nn.Module):
                 h = self._conv(st, sp["conv"], u, want_stats=True)
                 c = {"x": xin, "u": u} if save else None
             bctx.append(c)
-        assert len(hs) == 0 and ri == nrb
+        assert (len(hs) == 0 or self.up_extra != 1) and ri == nrb
+        del n_skips
         a, sums = self._gn_fwd(h, None, self.tail[0], act=1)
         eps = self._conv(st, st.tail, a, out_nchw=True)
         if save:
@@ -768,8 +928,7 @@ class UNetBase(nn.Module):
         bctx = ctx["bctx"]
         mods = list(self.downblocks) + list(self.middleblocks) + list(self.upblocks)
         n_down = len(self.downblocks)
-        dskip = {}                      # index into hs -> gradient w.r.t. that skip tensor
-        next_skip = 0                   # up blocks consume hs from the end; in reverse order from the start
+        dskip = {}                      # index into the down path's skip list -> gradient w.r.t. that skip tensor
         for li in range(len(mods) - 1, -1, -1):
             mod, c = mods[li], bctx[li]
             is_up = li >= n_down + len(self.middleblocks)
@@ -788,8 +947,11 @@ class UNetBase(nn.Module):
                         else psp["proj"] if "proj" in psp else psp["conv2"]
                 d_h, d_sk = self._res_bwd(st, mod, c, d_h, d_emb_all, acc0, prev_spec=prev_spec)
                 if is_up:
-                    dskip[next_skip] = d_sk
-                    next_skip += 1
+                    if c["skip_small"] is not None:          # the skip was resized by nearest interpolation: sum the blocks back
+                        small = torch.empty(c["skip_small"], dtype=d_sk.dtype, device=dev)
+                        ops.upsample_nearest_bwd(d_sk, small)
+                        d_sk = small
+                    dskip[c["skip_idx"]] = d_sk
             elif isinstance(mod, DownSample):
                 sp = st.blocks[id(mod)]["down"]
                 self._wgrad(st, sp, c["x"], None, d_h)
@@ -808,7 +970,8 @@ class UNetBase(nn.Module):
         self._wgrad(st, st.head, ctx["x"], None, d_h, in_nchw=not st.pad_io)
         # ---- data parallel: every packed weight and bias gradient is final here; their exchange runs under the embedding-path
         #      kernels below (only the small directly-written prefix of the flat buffer has to wait for those) ----
-        if reducer is not None:
+        late_conv = self.image_cond and "labels" in ctx      # the condition encoder's convolutions are still to come
+        if reducer is not None and not late_conv:
             self._join_side(st)
             reducer.flush(st.gpk[st.n_dw:])
         # ---- embedding path ----
@@ -827,28 +990,41 @@ class UNetBase(nn.Module):
         d_e0 = torch.empty_like(e0)
         ops.linear_bwd_x(d_e1, te[1].weight, None, d_e0)
         ops.embedding_bwd(d_e0, ctx["t"], gv(te[0].weight))
-        if "labels" in ctx:
-            ce = self.cond_embedding.condEmbedding
+        if ctx.get("cond_zero"):
+            # cemb = 0: the cond_proj weights get a zero gradient (Swish(0) = 0), their biases the column sums
+            ops.linear_bwd_w(d_emb_all, ctx["cemb"], fg[st.o_cw: st.o_cw + st.emb_total * self.tdim], fg[st.o_cb: st.o_cb + st.emb_total], in_swish=True)
+        elif "labels" in ctx:
+            if self.image_cond:
+                lin1, lin2 = self.cond_embedding.linear1, self.cond_embedding.linear2
+            else:
+                ce = self.cond_embedding.condEmbedding
+                lin1, lin2 = ce[1], ce[3]
             cemb, c1, c0 = ctx["cemb"], ctx["c1"], ctx["c0"]
             w_c = st.flat[st.o_cw: st.o_cw + st.emb_total * self.tdim].view(st.emb_total, self.tdim)
             ops.linear_bwd_w(d_emb_all, cemb, fg[st.o_cw: st.o_cw + st.emb_total * self.tdim], fg[st.o_cb: st.o_cb + st.emb_total], in_swish=True)
             d_cemb = torch.empty_like(cemb)
             ops.linear_bwd_x(d_emb_all, w_c, cemb, d_cemb)
-            ops.linear_bwd_w(d_cemb, c1, gv(ce[3].weight), gv(ce[3].bias), in_swish=True)
+            ops.linear_bwd_w(d_cemb, c1, gv(lin2.weight), gv(lin2.bias), in_swish=True)
             d_c1 = torch.empty_like(c1)
-            ops.linear_bwd_x(d_cemb, ce[3].weight, c1, d_c1)
-            ops.linear_bwd_w(d_c1, c0, gv(ce[1].weight), gv(ce[1].bias))
+            ops.linear_bwd_x(d_cemb, lin2.weight, c1, d_c1)
+            ops.linear_bwd_w(d_c1, c0, gv(lin1.weight), gv(lin1.bias))
             d_c0 = torch.empty_like(c0)
-            ops.linear_bwd_x(d_c1, ce[1].weight, None, d_c0)
-            ops.embedding_bwd(d_c0, ctx["labels"], gv(ce[0].weight), padding_idx=0)
+            ops.linear_bwd_x(d_c1, lin1.weight, None, d_c0)
+            if self.image_cond:
+                self._cond_bwd(st, ctx, d_c0)
+            else:
+                ops.embedding_bwd(d_c0, ctx["labels"], gv(ce[0].weight), padding_idx=0)
         # ---- data parallel: the directly written part of the flat buffer (GroupNorm, Linear, embedding tables); then the
         #      compute stream waits for every exchange of this step ----
         self._join_side(st)
         if reducer is not None:
-            reducer.finish(fg[:st.n_direct])
+            if late_conv:
+                reducer.finish(st.gpk[st.n_dw:], fg[:st.n_direct])
+            else:
+                reducer.finish(fg[:st.n_direct])
         # ---- packed conv gradients -> parameter layouts ----
         ops.scatter_unpack(st.gpk, st.inv, fg)
-        used_cond = "labels" in ctx
+        used_cond = "labels" in ctx or bool(ctx.get("cond_zero"))
         grads = []
         for p in st.order:
             if not p.requires_grad:
@@ -881,9 +1057,9 @@ class _UNetFunction(torch.autograd.Function):
     will receive a gradient — sees them as unused, as it does in the reference."""
 
     @staticmethod
-    def forward(fctx, net, x, t, labels, *params):
+    def forward(fctx, net, x, t, labels, context_zero, *params):
         with torch.no_grad():
-            eps, ctx = net._run_forward(x.detach(), t, labels, save=True)
+            eps, ctx = net._run_forward(x.detach(), t, labels, save=True, context_zero=context_zero)
         fctx.net, fctx.hd_ctx, fctx.param_ids = net, ctx, [id(p) for p in params]
         return eps
 
@@ -897,28 +1073,36 @@ class _UNetFunction(torch.autograd.Function):
             grads, used_cond = net._run_backward(ctx, d_eps)
         st = net._state
         by_id = {id(p): g for p, g in zip(st.order, grads)}
-        return (None, None, None, None) + tuple(by_id[i] for i in fctx.param_ids)
+        return (None, None, None, None, None) + tuple(by_id[i] for i in fctx.param_ids)
 
 
-def _apply(net, x, t, labels):
+def _apply(net, x, t, labels, context_zero=False):
+    """The autograd node's tensor inputs are the parameters this forward USES (and that require a gradient bookkeeping-wise)."""
     st = net._get_state()
     params = st.order
-    if labels is None:
+    skip = set()
+    if net.image_cond:
+        if context_zero or labels is None:       # cemb = 0: the condition encoder is not evaluated
+            skip = {id(q) for q in net.cond_embedding.parameters()}
+    elif labels is None:
         skip = {id(q) for rb in net._resblocks() for q in rb.cond_proj.parameters()}
+    if skip:
         params = [p for p in params if id(p) not in skip]
-    return _UNetFunction.apply(net, x, t, labels, *params)
+    return _UNetFunction.apply(net, x, t, labels, context_zero, *params)
 
 
 # route UNetBase.forward through the single autograd node
-def _forward(self, x, t, labels=None):
-    if self.num_labels is None:
+def _forward(self, x, t, labels=None, context_zero=False):
+    if self.image_cond:
+        pass                                     # DynamicUNet: labels is an image or None (diffusion/Model.py:475-484)
+    elif self.num_labels is None:
         assert labels is None, "unconditional UNet takes (x, t)"
     else:
         assert labels is not None, "conditional UNet takes (x, t, labels)"
     st = self._get_state()
     if torch.is_grad_enabled() and any(p.requires_grad for p in st.order):
-        return _apply(self, x, t, labels)
-    eps, _ = self._run_forward(x, t, labels, save=False)
+        return _apply(self, x, t, labels, context_zero)
+    eps, _ = self._run_forward(x, t, labels, save=False, context_zero=context_zero)
     return eps
 
 

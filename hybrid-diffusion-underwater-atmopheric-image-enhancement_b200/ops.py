@@ -57,7 +57,7 @@ class CudaOps:
 
     # ---- convolution family -------------------------------------------------------------
     def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0,
-             Cout_pad=None, chan_sums=None):
+             Cout_pad=None, chan_sums=None, quiet=False):
         """out = conv_k(view(x0|x1, P_in)) + bias + emb[:, :, None, None] + res, logical stride 1, 'same' padding.
         w: packed [CoutL][k*k][CinL] in the compute dtype.  H, W are the LOGICAL spatial dims.
         `alg_frac`: share of the packed taps that are real reference taps (space-to-depth views carry zeros);
@@ -82,7 +82,7 @@ class CudaOps:
             self.tc_launches += 1
             self._t1(e0, "conv_tc", flops)
             return True if chan_sums is not None else None      # True: the per-channel statistics were produced
-        if self.use_tc and dt == BF16:
+        if self.use_tc and dt == BF16 and not quiet:
             _warn_cuda_core("conv", f"C={C0}+{C1} P_in={P_in} Cout={Cout} P_out={P_out} H={H} W={W} k={k}")
         rc = lib.hd_conv_simt(dt, _p(x0), C0, _p(x1), C1, P_in, int(in_nchw), _p(w), _p(bias), _p(emb),
                               0 if emb is None else emb.stride(0), _p(res), _p(out), Cout, P_out, nchw_c,
@@ -91,7 +91,8 @@ class CudaOps:
         self.launches += 1
         self._t1(e0, "conv_simt", flops)
 
-    def wgrad(self, x0, x1, P_in, dy, P_dy, dw, N, H, W, k, dtype, in_nchw=False, dy_nchw=False, workspace=None, alg_frac=1.0):
+    def wgrad(self, x0, x1, P_in, dy, P_dy, dw, N, H, W, k, dtype, in_nchw=False, dy_nchw=False, workspace=None, alg_frac=1.0,
+              quiet=False):
         """dw[CoutL][k*k][CinL] (fp32, overwritten) = sum over pixels of dy (x) shifted input."""
         dt = _DT[dtype]
         C0 = x0.shape[1] if in_nchw else x0.shape[-1]
@@ -112,7 +113,7 @@ class CudaOps:
             self.tc_launches += 1
             self._t1(e0, "wgrad_tc", flops)
             return
-        if self.use_tc and dt == BF16:
+        if self.use_tc and dt == BF16 and not quiet:
             _warn_cuda_core("wgrad", f"C={C0}+{C1} P_in={P_in} Cdy={Cdy} P_dy={P_dy} H={H} W={W} k={k}")
         rc = lib.hd_wgrad_simt(dt, _p(x0), C0, _p(x1), C1, P_in, int(in_nchw), _p(dy), Cdy, P_dy, int(dy_nchw),
                                _p(dw), N, H, W, k, _stream())
@@ -165,6 +166,29 @@ class CudaOps:
                    "hd_mha_bwd")
         self.launches += 2
         self._t1(e0, "mha_bwd", 8.0 * N * S * S * C)
+
+    # ---- hybrid pipeline helpers -----------------------------------------------------------
+    def upsample_nearest(self, x, out):
+        """NHWC [N, H, W, C] -> out [N, fy H, fx W, C] (F.interpolate(mode="nearest") by integer factors)."""
+        N, H, W, C = x.shape
+        fy, fx = out.shape[1] // H, out.shape[2] // W
+        assert out.shape == (N, fy * H, fx * W, C)
+        _lib.check(self.lib.hd_upsample_nearest(_DT[x.dtype], _p(x), _p(out), N, H, W, C, fy, fx, _stream()), "hd_upsample_nearest")
+        self.launches += 1
+
+    def upsample_nearest_bwd(self, dout, din):
+        N, H, W, C = din.shape
+        fy, fx = dout.shape[1] // H, dout.shape[2] // W
+        assert dout.shape == (N, fy * H, fx * W, C)
+        _lib.check(self.lib.hd_upsample_nearest_bwd(_DT[din.dtype], _p(dout), _p(din), N, H, W, C, fy, fx, _stream()), "hd_upsample_nearest_bwd")
+        self.launches += 1
+
+    def image_affine(self, x, out, scale, shift):
+        """out (fp32) = x * scale + shift for a uint8 or fp32 image tensor of any shape (contiguous)."""
+        assert x.dtype in (torch.uint8, torch.float32) and x.is_contiguous() and out.dtype == torch.float32
+        _lib.check(self.lib.hd_image_affine(_p(x), int(x.dtype == torch.uint8), _p(out), float(scale), float(shift), x.numel(), _stream()),
+                   "hd_image_affine")
+        self.launches += 1
 
     # ---- GroupNorm family ----------------------------------------------------------------
     def gn_stats(self, x0, x1, N, HW, G, sums):

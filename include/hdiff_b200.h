@@ -86,6 +86,13 @@ int hd_mha_fwd(int dtype, const void* qkv, void* out, float* lse, int N, int S, 
 int hd_mha_bwd(int dtype, const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
                int N, int S, int C, int heads, hd_stream_t stream);
 
+/* ---- hybrid (image-conditioned) pipeline helpers.  Nearest-neighbour up-sampling of a skip tensor by an integer factors (fy, fx) and its
+ *      backward (DynamicUNet's skip fix-up, diffusion/Model.py:506-510), NHWC [N][H][W][C] -> [N][fy H][fx W][C]; image scaling
+ *      out = in * scale + shift from uint8 or fp32 (hybrid trainer / sampler, diffusion/Diffusion.py:56-57,221). ---- */
+int hd_upsample_nearest(int dtype, const void* in, void* out, int N, int H, int W, int C, int fy, int fx, hd_stream_t stream);
+int hd_upsample_nearest_bwd(int dtype, const void* dout, void* din, int N, int H, int W, int C, int fy, int fx, hd_stream_t stream);
+int hd_image_affine(const void* in, int src_u8, float* out, float scale, float shift, int64_t n, hd_stream_t stream);
+
 /* ---- GroupNorm(32) + Swish (+ Dropout): ModelCondition.py:128-129,141-143,95,249-250.  Two-source input
  *      (C0 | C1 channels) fuses torch.cat :271 into the normalisation.  sums/gsums = [N][G][2] fp64. ---- */
 int hd_gn_stats(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, double* sums,

@@ -92,6 +92,18 @@ def model_condition():
     return _cache["mc"]
 
 
+def diffusion_model():
+    """diffusion/Model.py, as is (DynamicUNet :382-517, the image ConditionalEmbedding :110-167, the MHA ResBlock :267-312)."""
+    if "dm" not in _cache:
+        if "telnetlib" not in sys.modules:
+            try:
+                import telnetlib  # noqa: F401
+            except Exception:
+                sys.modules["telnetlib"] = types.ModuleType("telnetlib")
+        _cache["dm"] = _load_by_path("_ref_diffusion_Model", "diffusion/Model.py")
+    return _cache["dm"]
+
+
 def assemble_unet(T, ch, ch_mult, attn, num_res_blocks, dropout, num_labels=None) -> nn.Module:
     """The F1 composition, made only of reference classes (ResBlock_old, AttnBlock, DownSample,
     UpSample, TimeEmbedding, ConditionalEmbedding) in the topology of ModelCondition.py:213-276."""

@@ -353,3 +353,26 @@ def train_step(trainer, optimizer, x_0, labels=None, grad_clip=1.0):
     torch.nn.utils.clip_grad_norm_(trainer.model.parameters(), grad_clip)
     optimizer.step()
     return loss
+
+
+def hybrid_trainer_forward(model, sqrt_alphas_bar, sqrt_one_minus_alphas_bar, T, gt_images, input_image):
+    """ORACLE restatement of the hybrid trainer's forward up to the noise MSE (diffusion/Diffusion.py:54-96; the class itself
+    cannot be constructed here: its ctor loads DINOv2 through torch.hub and moves it to CUDA, :49-54).  Line for line:
+    :56-57 scaling, :61-62 t and noise, :63-65 q_sample, :67 six-channel input, :71-74 the 2 % coin (both branches leave the
+    model's default context_zero=True in force), :89 unreduced MSE, :93-94 y_0 reconstruction.  Parity of this restatement is
+    unpinned (no reference run possible); the model inside it is the reference's own DynamicUNet."""
+    input_image = (input_image.float() / 255.0) * 2 - 1
+    gt_images = (gt_images.float() / 255.0) * 2 - 1
+    t = torch.randint(T, size=(gt_images.shape[0],), device=gt_images.device)
+    noise = torch.randn_like(gt_images, dtype=torch.float32)
+    y_t = (extract(sqrt_alphas_bar, t, gt_images.shape) * gt_images +
+           extract(sqrt_one_minus_alphas_bar, t, gt_images.shape) * noise)
+    inp = torch.cat([input_image, y_t], dim=1).float()
+    if torch.rand(1) < 0.02:
+        noise_pred = model(inp, t, gt_images, context_zero=True)
+    else:
+        noise_pred = model(inp, t, gt_images)
+    mse_loss = F.mse_loss(noise_pred, noise, reduction='none')
+    y_0_pred = 1 / extract(sqrt_alphas_bar, t, gt_images.shape) * (
+        y_t - extract(sqrt_one_minus_alphas_bar, t, gt_images.shape) * noise_pred).float() / 255.0
+    return mse_loss, y_0_pred

@@ -42,11 +42,14 @@ class EmuOps:
     # ---- convolution family ----
     def _logical_in(self, x0, x1, P_in, in_nchw):
         if in_nchw:
+            if P_in == 2:       # 2x2 space-to-depth view of an NCHW image, logical channel order (py, px, c)
+                N, C, PH, PW = x0.shape
+                return x0.float().view(N, C, PH // 2, 2, PW // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(N, 4 * C, PH // 2, PW // 2)
             return x0.float()
         x = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
         return to_logical(x, P_in).permute(0, 3, 1, 2).float()
 
-    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0, Cout_pad=None, chan_sums=None):
+    def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0, Cout_pad=None, chan_sums=None, quiet=False):
         xin = self._logical_in(x0, x1, P_in, in_nchw)
         CinL = xin.shape[1]
         CoutL = w.numel() // (k * k * CinL)
@@ -69,7 +72,7 @@ class EmuOps:
             return True
         return None
 
-    def wgrad(self, x0, x1, P_in, dy, P_dy, dw, N, H, W, k, dtype, in_nchw=False, dy_nchw=False, workspace=None, alg_frac=1.0):
+    def wgrad(self, x0, x1, P_in, dy, P_dy, dw, N, H, W, k, dtype, in_nchw=False, dy_nchw=False, workspace=None, alg_frac=1.0, quiet=False):
         xin = self._logical_in(x0, x1, P_in, in_nchw)
         g = dy.float() if dy_nchw else to_logical(dy, P_dy).permute(0, 3, 1, 2).float()
         CinL, CoutL = xin.shape[1], g.shape[1]
@@ -98,6 +101,21 @@ class EmuOps:
             o.backward(dout.float().view(N, S, C))
         dqkv.copy_(x.grad.view(dqkv.shape).to(dqkv.dtype))
         self.launches += 3
+
+    def upsample_nearest(self, x, out):
+        fy, fx = out.shape[1] // x.shape[1], out.shape[2] // x.shape[2]
+        out.copy_(x.repeat_interleave(fy, dim=1).repeat_interleave(fx, dim=2))
+        self.launches += 1
+
+    def upsample_nearest_bwd(self, dout, din):
+        N, H, W, C = din.shape
+        fy, fx = dout.shape[1] // H, dout.shape[2] // W
+        din.copy_(dout.float().view(N, H, fy, W, fx, C).sum(dim=(2, 4)).to(din.dtype))
+        self.launches += 1
+
+    def image_affine(self, x, out, scale, shift):
+        out.copy_(x.float() * scale + shift)
+        self.launches += 1
 
     def mha_fwd(self, qkv, out, lse, N, S, C, heads):
         hd = C // heads
