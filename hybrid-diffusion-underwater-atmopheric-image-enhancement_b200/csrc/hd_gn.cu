@@ -72,20 +72,43 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     return done != 0;
 }
 
+// Ring position, kept across the segments (images) a CTA walks.
+struct Cursor { int s = 0; uint32_t ph = 0; bool wrapped = false; };
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }     // the eight consumer warps only
+
+// A CTA's share of the batch is one contiguous range of the flattened pixel axis [0, N * HW): `seg(n, p0, p1)` is called for
+// every image the range touches.  One wave of CTAs covers the batch exactly (a per-image split leaves floor(444 / N) * N of the
+// 444 resident CTAs busy: 6 % idle at N = 32).
+template <typename F>
+__device__ __forceinline__ void for_each_segment(int per, int total, int HW, F seg) {       // N * HW < 2^31 (checked on the host)
+    int g0 = (int)blockIdx.x * per;
+    const int g1 = min(g0 + per, total);
+    int n = g0 / HW, p0 = g0 - n * HW;
+    while (g0 < g1) {
+        const int p1 = min(HW, p0 + (g1 - g0));
+        seg(n, p0, p1);
+        g0 += p1 - p0;
+        ++n; p0 = 0;
+    }
+}
+
 // producer lane: tiles of image n, pixels [p0, p1).  No divisions: (stage, phase) advance incrementally.
-__device__ __forceinline__ void produce(const Ring& r, const RingState& rs, int n, int HW, int p0, int p1) {
+__device__ __forceinline__ void produce(const Ring& r, const RingState& rs, Cursor& cu, uint32_t bpp_sum, int n, int HW, int p0, int p1) {
+    for (int p = p0; p < p1; p += r.TP) {
+        if (cu.wrapped && !mbar_try(rs.empty + cu.s, cu.ph ^ 1u)) mbar_wait(rs.empty + cu.s, cu.ph ^ 1u);    // consumers released the previous use
+        const uint32_t npx = (uint32_t)min(r.TP, p1 - p);
+        mbar_arrive_expect_tx(rs.full + cu.s, npx * bpp_sum);
+        uint8_t* dst = rs.buf + (size_t)cu.s * r.stage_bytes;
+        for (int k = 0; k < r.nstreams; ++k)
+            bulk_g2s(dst + r.off[k], r.base[k] + ((size_t)n * HW + p) * r.bpp[k], npx * r.bpp[k], rs.full + cu.s);
+        if (++cu.s == r.stages) { cu.s = 0; cu.ph ^= 1u; cu.wrapped = true; }
+    }
+}
+__device__ __forceinline__ void produce_all(const Ring& r, const RingState& rs, int per, int total, int HW) {
     uint32_t bpp_sum = 0;
     for (int k = 0; k < r.nstreams; ++k) bpp_sum += r.bpp[k];
-    int s = 0; uint32_t ph = 0; bool wrapped = false;
-    for (int p = p0; p < p1; p += r.TP) {
-        if (wrapped && !mbar_try(rs.empty + s, ph ^ 1u)) mbar_wait(rs.empty + s, ph ^ 1u);    // consumers released the previous use
-        const uint32_t npx = (uint32_t)min(r.TP, p1 - p);
-        mbar_arrive_expect_tx(rs.full + s, npx * bpp_sum);
-        uint8_t* dst = rs.buf + (size_t)s * r.stage_bytes;
-        for (int k = 0; k < r.nstreams; ++k)
-            bulk_g2s(dst + r.off[k], r.base[k] + ((size_t)n * HW + p) * r.bpp[k], npx * r.bpp[k], rs.full + s);
-        if (++s == r.stages) { s = 0; ph ^= 1u; wrapped = true; }
-    }
+    Cursor cu;
+    for_each_segment(per, total, HW, [&](int n, int p0, int p1) { produce(r, rs, cu, bpp_sum, n, HW, p0, p1); });
 }
 
 __device__ __forceinline__ uint2 lds8(const uint8_t* p) { return *reinterpret_cast<const uint2*>(p); }
@@ -148,58 +171,63 @@ __device__ __forceinline__ void mask4(const GnArgs& g, uint32_t thr2, uint32_t p
 // (partial) tile checks each slot.  (stage, phase) advance incrementally: an integer division per tile costs more than the
 // tile's arithmetic.
 template <int KPT, typename Load, typename Math>
-__device__ __forceinline__ void consume(const Ring& r, const RingState& rs, const Map& m, int p0, int p1, Load load, Math math) {
-    int s = 0; uint32_t ph = 0;
-    const uint8_t* sb = rs.buf;
+__device__ __forceinline__ void consume(const Ring& r, const RingState& rs, const Map& m, Cursor& cu, int p0, int p1, Load load, Math math) {
     const bool lane0 = (threadIdx.x & 31) == 0;
     int p = p0;
     for (; p + r.TP <= p1; p += r.TP) {
-        if (!mbar_try(rs.full + s, ph)) mbar_wait(rs.full + s, ph);
+        if (!mbar_try(rs.full + cu.s, cu.ph)) mbar_wait(rs.full + cu.s, cu.ph);
+        const uint8_t* sb = rs.buf + (size_t)cu.s * r.stage_bytes;
         if (m.active) {
 #pragma unroll
             for (int k = 0; k < KPT; ++k) load(sb, k);
         }
         __syncwarp();
-        if (lane0) mbar_arrive(rs.empty + s);
+        if (lane0) mbar_arrive(rs.empty + cu.s);
         if (m.active) {
 #pragma unroll
             for (int k = 0; k < KPT; ++k) math(p + m.sub + k * m.ppi, k);
         }
-        if (++s == r.stages) { s = 0; ph ^= 1u; sb = rs.buf; } else sb += r.stage_bytes;
+        if (++cu.s == r.stages) { cu.s = 0; cu.ph ^= 1u; }
     }
     if (p < p1) {
         const int npx = p1 - p;
-        mbar_wait(rs.full + s, ph);
+        mbar_wait(rs.full + cu.s, cu.ph);
+        const uint8_t* sb = rs.buf + (size_t)cu.s * r.stage_bytes;
         if (m.active) {
 #pragma unroll
             for (int k = 0; k < KPT; ++k) if (m.sub + k * m.ppi < npx) load(sb, k);
         }
         __syncwarp();
-        if (lane0) mbar_arrive(rs.empty + s);
+        if (lane0) mbar_arrive(rs.empty + cu.s);
         if (m.active) {
 #pragma unroll
             for (int k = 0; k < KPT; ++k) if (m.sub + k * m.ppi < npx) math(p + m.sub + k * m.ppi, k);
         }
+        if (++cu.s == r.stages) { cu.s = 0; cu.ph ^= 1u; }
     }
 }
 
 // ------------------------------- statistics -------------------------------------------------
-constexpr int kKPTStats = 8, kKPTFwd = 8, kKPTReduce = 4;
-__global__ void __launch_bounds__(kThreads, 3) gn2_stats_kernel(GnArgs g, Ring r, int ppb, double* sums) {
+constexpr int kKPTStats = 8, kKPTFwd = 4, kKPTReduce = 4;
+__global__ void __launch_bounds__(kThreads, 3) gn2_stats_kernel(GnArgs g, Ring r, int per, double* sums) {
     extern __shared__ __align__(128) uint8_t dyn[];
     __shared__ float sg[64][2];
     RingState rs; rs.init(r, dyn);
-    const int n = blockIdx.y;
-    if (threadIdx.x < 64) { sg[threadIdx.x][0] = 0.f; sg[threadIdx.x][1] = 0.f; }
     __syncthreads();
-    const int p0 = blockIdx.x * ppb, p1 = min(p0 + ppb, g.HW);
+    const int total = g.N * g.HW;
     if (threadIdx.x >= kConsumers) {
-        if (threadIdx.x == kConsumers) produce(r, rs, n, g.HW, p0, p1);
-    } else {
-        const Map m(g, r);
+        if (threadIdx.x == kConsumers) produce_all(r, rs, per, total, g.HW);
+        return;
+    }
+    const Map m(g, r);
+    const int cpg = g.C / g.G;
+    Cursor cu;
+    for_each_segment(per, total, g.HW, [&](int n, int p0, int p1) {
+        if (threadIdx.x < 64) { sg[threadIdx.x][0] = 0.f; sg[threadIdx.x][1] = 0.f; }
+        consumer_sync();
         float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
         uint2 xr[kKPTStats];
-        consume<kKPTStats>(r, rs, m, p0, p1,
+        consume<kKPTStats>(r, rs, m, cu, p0, p1,
                 [&](const uint8_t* sb, int k) { xr[k] = lds8(sb + m.xo + k * m.xstep); },
                 [&](int, int k) {
                     float v[4]; unpack4(xr[k], v);
@@ -207,66 +235,70 @@ __global__ void __launch_bounds__(kThreads, 3) gn2_stats_kernel(GnArgs g, Ring r
                     for (int i = 0; i < 4; ++i) { s[i] += v[i]; ss[i] = fmaf(v[i], v[i], ss[i]); }
                 });
         if (m.active) {
-            const int cpg = g.C / g.G;
 #pragma unroll
             for (int k = 0; k < 4; ++k) { const int gi = (m.c + k) / cpg; atomicAdd(&sg[gi][0], s[k]); atomicAdd(&sg[gi][1], ss[k]); }
         }
-    }
-    __syncthreads();
-    if (threadIdx.x < g.G) {
-        atomicAdd(sums + ((size_t)n * g.G + threadIdx.x) * 2, (double)sg[threadIdx.x][0]);
-        atomicAdd(sums + ((size_t)n * g.G + threadIdx.x) * 2 + 1, (double)sg[threadIdx.x][1]);
-    }
+        consumer_sync();
+        if (threadIdx.x < g.G) {
+            atomicAdd(sums + ((size_t)n * g.G + threadIdx.x) * 2, (double)sg[threadIdx.x][0]);
+            atomicAdd(sums + ((size_t)n * g.G + threadIdx.x) * 2 + 1, (double)sg[threadIdx.x][1]);
+        }
+        consumer_sync();
+    });
 }
 
 // ------------------------------- apply (forward) --------------------------------------------
 // out = drop(act(x * a + b));  ACT: swish through tanh.approx (|abs error| <= 5e-4 |z|/2, below the bf16 rounding of the
 // tensor's O(1) values)
 template <bool ACT, bool DROP>
-__global__ void __launch_bounds__(kThreads, 3) gn2_apply_kernel(GnArgs g, Ring r, int ppb, bf16* out) {
+__global__ void __launch_bounds__(kThreads, 3) gn2_apply_kernel(GnArgs g, Ring r, int per, bf16* out) {
     extern __shared__ __align__(128) uint8_t dyn[];
     __shared__ float s_mean[64], s_rstd[64];
     RingState rs; rs.init(r, dyn);
-    const int n = blockIdx.y;
-    load_stats(g, n, s_mean, s_rstd);
     __syncthreads();
-    const int p0 = blockIdx.x * ppb, p1 = min(p0 + ppb, g.HW);
+    const int total = g.N * g.HW;
     if (threadIdx.x >= kConsumers) {
-        if (threadIdx.x == kConsumers) produce(r, rs, n, g.HW, p0, p1);
+        if (threadIdx.x == kConsumers) produce_all(r, rs, per, total, g.HW);
         return;
     }
     const Map m(g, r);
     const int cpg = g.C / g.G;
     const float keep = DROP ? 1.f / (1.f - g.p_drop) : 1.f;
-    float A[4], B[4];
-    if (m.active) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int gi = (m.c + k) / cpg;
-            const float a = s_rstd[gi] * g.gamma[m.c + k];
-            const float sc = ACT ? 0.5f : keep;
-            A[k] = sc * a;
-            B[k] = sc * (g.beta[m.c + k] - s_mean[gi] * a);
-        }
-    }
     const uint32_t thr2 = hd_dropout_thr15(g.p_drop) * 0x00010001u;
-    bf16* op = out + (size_t)n * g.HW * g.C + m.c;
-    const uint32_t pix0 = (uint32_t)n * (uint32_t)g.HW;
-    uint2 xr[kKPTFwd];
-    consume<kKPTFwd>(r, rs, m, p0, p1,
-            [&](const uint8_t* sb, int k) { xr[k] = lds8(sb + m.xo + k * m.xstep); },
-            [&](int p, int k) {
-                float v[4], y[4]; unpack4(xr[k], v);
+    Cursor cu;
+    for_each_segment(per, total, g.HW, [&](int n, int p0, int p1) {
+        consumer_sync();                               // the previous image's statistics are no longer read
+        load_stats(g, n, s_mean, s_rstd);
+        consumer_sync();
+        float A[4], B[4];
+        if (m.active) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float h = fmaf(v[i], A[i], B[i]);
-                    if (ACT) { const float hk = DROP ? h * keep : h; y[i] = fmaf(hk, tanh_fast(h), hk); }
-                    else y[i] = h;
-                }
-                uint2 o = make_uint2(pack2(y[0], y[1]), pack2(y[2], y[3]));
-                if (DROP) mask4(g, thr2, pix0 + (uint32_t)p, m.c, o);
-                *reinterpret_cast<uint2*>(op + (size_t)p * g.C) = o;
-            });
+            for (int k = 0; k < 4; ++k) {
+                const int gi = (m.c + k) / cpg;
+                const float a = s_rstd[gi] * g.gamma[m.c + k];
+                const float sc = ACT ? 0.5f : keep;
+                A[k] = sc * a;
+                B[k] = sc * (g.beta[m.c + k] - s_mean[gi] * a);
+            }
+        }
+        bf16* op = out + (size_t)n * g.HW * g.C + m.c;
+        const uint32_t pix0 = (uint32_t)n * (uint32_t)g.HW;
+        uint2 xr[kKPTFwd];
+        consume<kKPTFwd>(r, rs, m, cu, p0, p1,
+                [&](const uint8_t* sb, int k) { xr[k] = lds8(sb + m.xo + k * m.xstep); },
+                [&](int p, int k) {
+                    float v[4], y[4]; unpack4(xr[k], v);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float h = fmaf(v[i], A[i], B[i]);
+                        if (ACT) { const float hk = DROP ? h * keep : h; y[i] = fmaf(hk, tanh_fast(h), hk); }
+                        else y[i] = h;
+                    }
+                    uint2 o = make_uint2(pack2(y[0], y[1]), pack2(y[2], y[3]));
+                    if (DROP) mask4(g, thr2, pix0 + (uint32_t)p, m.c, o);
+                    *reinterpret_cast<uint2*>(op + (size_t)p * g.C) = o;
+                });
+    });
 }
 
 // ------------------------------- backward: shared element math ------------------------------
@@ -286,22 +318,27 @@ __device__ __forceinline__ float dd_of(float v, float d, float A, float B) {
 // Per channel: dgamma += sum dy' xhat, dbeta += sum dy'.  Per (n, group): gsums = (sum gamma dy', sum gamma dy' xhat).
 // streams: x0 [, x1], dy (last)
 template <bool ACT, bool DROP>
-__global__ void __launch_bounds__(kThreads, 3) gn2_bwd_reduce_kernel(GnArgs g, Ring r, int ppb, double* gsums, float* dgamma, float* dbeta) {
+__global__ void __launch_bounds__(kThreads, 3) gn2_bwd_reduce_kernel(GnArgs g, Ring r, int per, double* gsums, float* dgamma, float* dbeta) {
     extern __shared__ __align__(128) uint8_t dyn[];
     __shared__ float s_mean[64], s_rstd[64], sg[64][2];
     RingState rs; rs.init(r, dyn);
     float* s_ch = reinterpret_cast<float*>(dyn + 128 + (size_t)r.stages * r.stage_bytes);      // [2][C] behind the ring
-    const int n = blockIdx.y;
-    load_stats(g, n, s_mean, s_rstd);
-    if (threadIdx.x < 64) { sg[threadIdx.x][0] = 0.f; sg[threadIdx.x][1] = 0.f; }
-    for (int i = threadIdx.x; i < 2 * g.C; i += kThreads) s_ch[i] = 0.f;
     __syncthreads();
-    const int p0 = blockIdx.x * ppb, p1 = min(p0 + ppb, g.HW);
-    const int cpg = g.C / g.G;
+    const int total = g.N * g.HW;
     if (threadIdx.x >= kConsumers) {
-        if (threadIdx.x == kConsumers) produce(r, rs, n, g.HW, p0, p1);
-    } else {
-        const Map m(g, r);
+        if (threadIdx.x == kConsumers) produce_all(r, rs, per, total, g.HW);
+        return;
+    }
+    const Map m(g, r);
+    const int cpg = g.C / g.G;
+    const uint32_t thr2 = hd_dropout_thr15(g.p_drop) * 0x00010001u;
+    const uint32_t dyo = m.wide_off(g, r.off[r.nstreams - 1]), dstep = m.wide_step(g);
+    Cursor cu;
+    for_each_segment(per, total, g.HW, [&](int n, int p0, int p1) {
+        load_stats(g, n, s_mean, s_rstd);
+        if (threadIdx.x < 64) { sg[threadIdx.x][0] = 0.f; sg[threadIdx.x][1] = 0.f; }
+        for (int i = threadIdx.x; i < 2 * g.C; i += kConsumers) s_ch[i] = 0.f;
+        consumer_sync();
         float A[4], B[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
         if (m.active) {
 #pragma unroll
@@ -312,11 +349,9 @@ __global__ void __launch_bounds__(kThreads, 3) gn2_bwd_reduce_kernel(GnArgs g, R
                 B[k] = 0.5f * (g.beta[m.c + k] - s_mean[gi] * a);
             }
         }
-        const uint32_t thr2 = hd_dropout_thr15(g.p_drop) * 0x00010001u;
-        const uint32_t dyo = m.wide_off(g, r.off[r.nstreams - 1]), dstep = m.wide_step(g);
         const uint32_t pix0 = (uint32_t)n * (uint32_t)g.HW;
         uint2 xr[kKPTReduce], dr[kKPTReduce];
-        consume<kKPTReduce>(r, rs, m, p0, p1,
+        consume<kKPTReduce>(r, rs, m, cu, p0, p1,
                 [&](const uint8_t* sb, int k) { xr[k] = lds8(sb + m.xo + k * m.xstep); dr[k] = lds8(sb + dyo + k * dstep); },
                 [&](int p, int k) {
                     if (DROP) mask4(g, thr2, pix0 + (uint32_t)p, m.c, dr[k]);
@@ -339,13 +374,14 @@ __global__ void __launch_bounds__(kThreads, 3) gn2_bwd_reduce_kernel(GnArgs g, R
                 atomicAdd(&sg[gi][0], gam * t1); atomicAdd(&sg[gi][1], gam * sxh);
             }
         }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < g.C; i += kThreads) { atomicAdd(dgamma + i, s_ch[i]); atomicAdd(dbeta + i, s_ch[g.C + i]); }
-    if (threadIdx.x < g.G) {
-        atomicAdd(gsums + ((size_t)n * g.G + threadIdx.x) * 2, (double)sg[threadIdx.x][0]);
-        atomicAdd(gsums + ((size_t)n * g.G + threadIdx.x) * 2 + 1, (double)sg[threadIdx.x][1]);
-    }
+        consumer_sync();
+        for (int i = threadIdx.x; i < g.C; i += kConsumers) { atomicAdd(dgamma + i, s_ch[i]); atomicAdd(dbeta + i, s_ch[g.C + i]); }
+        if (threadIdx.x < g.G) {
+            atomicAdd(gsums + ((size_t)n * g.G + threadIdx.x) * 2, (double)sg[threadIdx.x][0]);
+            atomicAdd(gsums + ((size_t)n * g.G + threadIdx.x) * 2 + 1, (double)sg[threadIdx.x][1]);
+        }
+        consumer_sync();
+    });
 }
 
 // ------------------------------- backward, apply pass ---------------------------------------
@@ -358,55 +394,58 @@ struct GnBwdOut {
     int s_dy, s_add, s_acc0, s_acc1;                   // stream index of each operand (-1: absent)
 };
 template <bool ACT, bool DROP, int KPT>
-__global__ void __launch_bounds__(kThreads, 3) gn2_bwd_apply_kernel(GnArgs g, Ring r, int ppb, const double* gsums, GnBwdOut o) {
+__global__ void __launch_bounds__(kThreads, 3) gn2_bwd_apply_kernel(GnArgs g, Ring r, int per, const double* gsums, GnBwdOut o) {
     extern __shared__ __align__(128) uint8_t dyn[];
     __shared__ float s_mean[64], s_rstd[64], s_a[64], s_b[64];
     RingState rs; rs.init(r, dyn);
     float* s_cs = reinterpret_cast<float*>(dyn + 128 + (size_t)r.stages * r.stage_bytes);      // [C] behind the ring
-    const int n = blockIdx.y;
-    const bool want_cs = o.cs_total || o.cs_per_n;
-    if (want_cs) for (int i = threadIdx.x; i < g.C; i += kThreads) s_cs[i] = 0.f;
-    load_stats(g, n, s_mean, s_rstd);
-    if (threadIdx.x < g.G) {
-        const double cnt = (double)(g.C / g.G) * (double)g.HW;
-        s_a[threadIdx.x] = (float)(__ldcg(gsums + ((size_t)n * g.G + threadIdx.x) * 2) / cnt);
-        s_b[threadIdx.x] = (float)(__ldcg(gsums + ((size_t)n * g.G + threadIdx.x) * 2 + 1) / cnt);
-    }
     __syncthreads();
-    const int p0 = blockIdx.x * ppb, p1 = min(p0 + ppb, g.HW);
-    const int cpg = g.C / g.G;
+    const int total = g.N * g.HW;
     if (threadIdx.x >= kConsumers) {
-        if (threadIdx.x == kConsumers) produce(r, rs, n, g.HW, p0, p1);
-    } else {
-        const Map m(g, r);
-        // dd = K' dy' (K' = 2 for ACT, keep-scale missing): dx = A1 dd - C1 - v D1 with A1 = rstd gamma keep / K'
-        float A[4], B[4], A1[4], C1[4], D1[4], cs[4] = {0.f, 0.f, 0.f, 0.f};
-        const float keep = DROP ? 1.f / (1.f - g.p_drop) : 1.f;
+        if (threadIdx.x == kConsumers) produce_all(r, rs, per, total, g.HW);
+        return;
+    }
+    const Map m(g, r);
+    const int cpg = g.C / g.G;
+    const bool want_cs = o.cs_total || o.cs_per_n;
+    const float keep = DROP ? 1.f / (1.f - g.p_drop) : 1.f;
+    const uint32_t thr2 = hd_dropout_thr15(g.p_drop) * 0x00010001u;
+    const uint32_t dstep = m.wide_step(g);
+    const uint32_t dyo = m.wide_off(g, r.off[o.s_dy]);
+    constexpr bool EXTRA = KPT == 2;                   // the four-slot instantiation is launched without addends only
+    const bool has_add = EXTRA && o.s_add >= 0;
+    const uint32_t ado = has_add ? m.wide_off(g, r.off[o.s_add]) : 0u;
+    const int s_acc = m.first ? o.s_acc0 : o.s_acc1;
+    const bool has_acc = EXTRA && s_acc >= 0;
+    const uint32_t aco = has_acc ? r.off[s_acc] + (uint32_t)(m.sub * m.xs + m.cd) * 2u : 0u;
+    Cursor cu;
+    for_each_segment(per, total, g.HW, [&](int n, int p0, int p1) {
+        if (want_cs) for (int i = threadIdx.x; i < g.C; i += kConsumers) s_cs[i] = 0.f;
+        load_stats(g, n, s_mean, s_rstd);
+        if (threadIdx.x < g.G) {
+            const double cnt = (double)(g.C / g.G) * (double)g.HW;
+            s_a[threadIdx.x] = (float)(__ldcg(gsums + ((size_t)n * g.G + threadIdx.x) * 2) / cnt);
+            s_b[threadIdx.x] = (float)(__ldcg(gsums + ((size_t)n * g.G + threadIdx.x) * 2 + 1) / cnt);
+        }
+        consumer_sync();
+        // dd = K' dy' (K' = 2 for ACT, keep-scale missing): dx = A (keep dd) - C1 - v D1 with A = rstd gamma / K'.  ACT: the same A
+        // forms h = z / 2 (one array serves both, keep is applied to dd); no ACT: A carries the keep-scale itself.
+        float A[4], B[4], C1[4], D1[4], cs[4] = {0.f, 0.f, 0.f, 0.f};
         if (m.active) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int c = m.c + k, gi = c / cpg;
                 const float rstd = s_rstd[gi], mr = -s_mean[gi] * rstd, a = rstd * g.gamma[c];
-                A[k] = 0.5f * a;
+                A[k] = ACT ? 0.5f * a : keep * a;
                 B[k] = 0.5f * fmaf(mr, g.gamma[c], g.beta[c]);
-                A1[k] = (ACT ? 0.5f : 1.f) * keep * a;
                 C1[k] = rstd * (s_a[gi] + mr * s_b[gi]);
                 D1[k] = rstd * rstd * s_b[gi];
             }
         }
-        const uint32_t thr2 = hd_dropout_thr15(g.p_drop) * 0x00010001u;
-        const uint32_t dstep = m.wide_step(g);
-        const uint32_t dyo = m.wide_off(g, r.off[o.s_dy]);
-        constexpr bool EXTRA = KPT == 2;                   // the four-slot instantiation is launched without addends only
-        const bool has_add = EXTRA && o.s_add >= 0;
-        const uint32_t ado = has_add ? m.wide_off(g, r.off[o.s_add]) : 0u;
-        const int s_acc = m.first ? o.s_acc0 : o.s_acc1;
-        const bool has_acc = EXTRA && s_acc >= 0;
-        const uint32_t aco = has_acc ? r.off[s_acc] + (uint32_t)(m.sub * m.xs + m.cd) * 2u : 0u;
         bf16* op = (m.first ? o.dx0 : o.dx1) + (size_t)n * g.HW * m.xs + m.cd;
         const uint32_t pix0 = (uint32_t)n * (uint32_t)g.HW;
         uint2 xr[KPT], dr[KPT], ar[EXTRA ? KPT : 1], cr[EXTRA ? KPT : 1];
-        consume<KPT>(r, rs, m, p0, p1,
+        consume<KPT>(r, rs, m, cu, p0, p1,
                 [&](const uint8_t* sb, int k) {
                     xr[k] = lds8(sb + m.xo + k * m.xstep); dr[k] = lds8(sb + dyo + k * dstep);
                     if (EXTRA && has_add) ar[k] = lds8(sb + ado + k * dstep);
@@ -417,8 +456,9 @@ __global__ void __launch_bounds__(kThreads, 3) gn2_bwd_apply_kernel(GnArgs g, Ri
                     float v[4], d[4], res[4]; unpack4(xr[k], v); unpack4(dr[k], d);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float dd = dd_of<ACT>(v[i], d[i], A[i], B[i]);
-                        res[i] = fmaf(A1[i], dd, -fmaf(v[i], D1[i], C1[i]));
+                        float dd = dd_of<ACT>(v[i], d[i], A[i], B[i]);
+                        if (ACT && DROP) dd *= keep;
+                        res[i] = fmaf(A[i], dd, -fmaf(v[i], D1[i], C1[i]));
                     }
                     if (EXTRA && has_add) { float t[4]; unpack4(ar[k], t);
 #pragma unroll
@@ -430,22 +470,23 @@ __global__ void __launch_bounds__(kThreads, 3) gn2_bwd_apply_kernel(GnArgs g, Ri
 #pragma unroll
                     for (int i = 0; i < 4; ++i) cs[i] += res[i];
                 });
-        if (want_cs && m.active) {
+        if (want_cs) {
+            if (m.active) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) atomicAdd(&s_cs[m.c + k], cs[k]);
+                for (int k = 0; k < 4; ++k) atomicAdd(&s_cs[m.c + k], cs[k]);
+            }
+            consumer_sync();
+            for (int i = threadIdx.x; i < o.cs_n; i += kConsumers) {
+                if (o.cs_per_n) atomicAdd(o.cs_per_n + (int64_t)n * o.cs_ld + i, s_cs[i]);
+                if (o.cs_total) atomicAdd(o.cs_total + i, s_cs[i]);
+            }
         }
-    }
-    if (want_cs) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < o.cs_n; i += kThreads) {
-            if (o.cs_per_n) atomicAdd(o.cs_per_n + (int64_t)n * o.cs_ld + i, s_cs[i]);
-            if (o.cs_total) atomicAdd(o.cs_total + i, s_cs[i]);
-        }
-    }
+        consumer_sync();                               // shared statistics / partials are reused by the next image
+    });
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
-struct Plan { Ring r; int ppb, chunks; size_t smem; };
+struct Plan { Ring r; int per; int grid; size_t smem; };
 
 int add_stream(Ring& r, const void* base, int channels) {
     const int k = r.nstreams++;
@@ -453,7 +494,8 @@ int add_stream(Ring& r, const void* base, int channels) {
     r.bpp[k] = (uint32_t)channels * 2u;
     return k;
 }
-// TP pixels per tile (kKPT steps of ppi pixels), as many stages as fit the budget; one wave of CTAs (3 per SM)
+// TP pixels per tile (kpt steps of ppi pixels), as many stages as fit the budget; ONE wave of CTAs (3 per SM), each taking a
+// contiguous, tile-aligned share of the flattened pixel axis [0, N * HW)
 Plan finish_plan(Ring r, int N, int HW, int C, size_t tail_bytes, int kpt) {
     Plan pl;
     const int ppi = kConsumers / (C / 4);
@@ -465,15 +507,14 @@ Plan finish_plan(Ring r, int N, int HW, int C, size_t tail_bytes, int kpt) {
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
     r.stages = stages;
-    const int64_t resident = (int64_t)hd_num_sms() * 3;
-    int64_t chunks = resident / N;
-    const int64_t max_chunks = (HW + r.TP - 1) / r.TP;
-    if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks < 1) chunks = 1;
-    int64_t ppb = (HW + chunks - 1) / chunks;
-    ppb = (ppb + r.TP - 1) / r.TP * r.TP;
-    pl.chunks = (int)((HW + ppb - 1) / ppb);
-    pl.ppb = (int)ppb;
+    const int64_t total = (int64_t)N * HW;
+    int64_t ctas = (int64_t)hd_num_sms() * 3;
+    const int64_t tiles = (total + r.TP - 1) / r.TP;
+    if (ctas > tiles) ctas = tiles;
+    int64_t per = (total + ctas - 1) / ctas;
+    per = (per + r.TP - 1) / r.TP * r.TP;
+    pl.per = (int)per;
+    pl.grid = (int)((total + per - 1) / per);
     pl.r = r;
     pl.smem = 128 + (size_t)r.stages * r.stage_bytes + tail_bytes;
     return pl;
@@ -490,7 +531,7 @@ bool gn2_shape_ok(int C0, int C1, int G, int64_t HW, int N) {
     const int C = C0 + C1;
     // every stream's pixel row must be a multiple of 16 bytes (bulk copies): channel counts in multiples of 8
     return G > 0 && G <= 64 && C % G == 0 && C0 % 8 == 0 && C1 % 8 == 0 && C / 4 <= kConsumers && HW < (1ll << 31)
-        && (int64_t)N * HW * C < (1ll << 40) && N <= 65535;
+        && (int64_t)N * HW * C < (1ll << 40) && (int64_t)N * HW < (1ll << 31) - (1 << 20);
 }
 
 #define GN2_FLAGS(KERNEL, ...)                                                                                          \
@@ -524,7 +565,7 @@ int hd_gn2_stats(const void* in0, int C0, const void* in1, int C1, int N, int64_
     Ring r{}; add_stream(r, in0, C0); if (C1) add_stream(r, in1, C1);
     const Plan pl = finish_plan(r, N, (int)HW, g.C, 0, kKPTStats);
     int rc = set_smem(gn2_stats_kernel, pl.smem); if (rc) return rc;
-    gn2_stats_kernel<<<dim3(pl.chunks, N), kThreads, pl.smem, st>>>(g, pl.r, pl.ppb, sums);
+    gn2_stats_kernel<<<pl.grid, kThreads, pl.smem, st>>>(g, pl.r, pl.per, sums);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }
@@ -534,10 +575,10 @@ int hd_gn2_apply(const void* in0, int C0, const void* in1, int C1, int N, int64_
     GnArgs g{(const bf16*)in0, (const bf16*)in1, C0, C1, N, (int)HW, C0 + C1, G, sums, gamma, beta, eps, p_drop, hd_seed_mix(seed)};
     Ring r{}; add_stream(r, in0, C0); if (C1) add_stream(r, in1, C1);
     const Plan pl = finish_plan(r, N, (int)HW, g.C, 0, kKPTFwd);
-    const dim3 grid(pl.chunks, N);
+    const int grid = pl.grid;
     const bool drop = p_drop > 0.f;
     int rc = HD_OK;
-    GN2_FLAGS(gn2_apply_kernel, <<<grid, kThreads, pl.smem, st>>>(g, pl.r, pl.ppb, (bf16*)out));
+    GN2_FLAGS(gn2_apply_kernel, <<<grid, kThreads, pl.smem, st>>>(g, pl.r, pl.per, (bf16*)out));
     if (rc) return rc;
     HD_CHECK_LAUNCH();
     return HD_OK;
@@ -551,10 +592,10 @@ int hd_gn2_bwd_reduce(const void* in0, int C0, const void* in1, int C1, int N, i
     Ring r{}; add_stream(r, in0, C0); if (C1) add_stream(r, in1, C1);
     add_stream(r, dy, g.C);
     const Plan pl = finish_plan(r, N, (int)HW, g.C, 2 * g.C * sizeof(float), kKPTReduce);
-    const dim3 grid(pl.chunks, N);
+    const int grid = pl.grid;
     const bool drop = p_drop > 0.f;
     int rc = HD_OK;
-    GN2_FLAGS(gn2_bwd_reduce_kernel, <<<grid, kThreads, pl.smem, st>>>(g, pl.r, pl.ppb, gsums, dgamma, dbeta));
+    GN2_FLAGS(gn2_bwd_reduce_kernel, <<<grid, kThreads, pl.smem, st>>>(g, pl.r, pl.per, gsums, dgamma, dbeta));
     if (rc) return rc;
     HD_CHECK_LAUNCH();
     return HD_OK;
@@ -574,11 +615,11 @@ int hd_gn2_bwd_apply(const void* in0, int C0, const void* in1, int C1, int N, in
     // two operand streams per pixel (x, dy): four pixel slots per thread and tile; with addends: two (16 raw registers either way)
     const bool lean = !add && !acc0 && !(acc1 && C1);
     const Plan pl = finish_plan(r, N, (int)HW, g.C, g.C * sizeof(float), lean ? 4 : 2);
-    const dim3 grid(pl.chunks, N);
+    const int grid = pl.grid;
     const bool drop = p_drop > 0.f;
     int rc = HD_OK;
-    if (lean) GN2_FLAGS3(gn2_bwd_apply_kernel, 4, <<<grid, kThreads, pl.smem, st>>>(g, pl.r, pl.ppb, gsums, o));
-    else GN2_FLAGS3(gn2_bwd_apply_kernel, 2, <<<grid, kThreads, pl.smem, st>>>(g, pl.r, pl.ppb, gsums, o));
+    if (lean) GN2_FLAGS3(gn2_bwd_apply_kernel, 4, <<<grid, kThreads, pl.smem, st>>>(g, pl.r, pl.per, gsums, o));
+    else GN2_FLAGS3(gn2_bwd_apply_kernel, 2, <<<grid, kThreads, pl.smem, st>>>(g, pl.r, pl.per, gsums, o));
     if (rc) return rc;
     HD_CHECK_LAUNCH();
     return HD_OK;
