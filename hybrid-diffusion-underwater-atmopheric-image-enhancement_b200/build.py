@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhdiff_b200.so")
-SOURCES = ["hd_simt.cu", "hd_fused.cu", "hd_gn.cu", "hd_mha.cu", "hd_image.cu", "hd_conv_tc.cu", "hd_wgrad_tc.cu", "hd_attn_tc.cu", "hd_attn_wide_tc.cu"]
+SOURCES = ["hd_simt.cu", "hd_fused.cu", "hd_gn.cu", "hd_mha.cu", "hd_image.cu", "hd_metrics.cu", "hd_conv_tc.cu", "hd_wgrad_tc.cu", "hd_attn_tc.cu", "hd_attn_wide_tc.cu"]
 # lab build (`--lab`): the same sources with -DHDIFF_LAB (timing modes of the conv kernel) + the hardware probes -> libhdiff_b200_lab.so
 LAB_SOURCES = ["hd_probe.cu", "hd_probe2.cu"]
 LAB_LIB = os.path.join(HERE, "libhdiff_b200_lab.so")

@@ -93,6 +93,16 @@ int hd_upsample_nearest(int dtype, const void* in, void* out, int N, int H, int 
 int hd_upsample_nearest_bwd(int dtype, const void* dout, void* din, int N, int H, int W, int C, int fy, int fx, hd_stream_t stream);
 int hd_image_affine(const void* in, int src_u8, float* out, float scale, float shift, int64_t n, hd_stream_t stream);
 
+/* ---- input pipeline and evaluation metrics of the product pipeline, 8-bit images.
+ *      hd_resize_bilinear_u8: cv2.resize(img, (DW, DH), INTER_LINEAR) bit-exact, src [N][SH][SW][C] -> dst [N][DH][DW][C] or, chw != 0,
+ *      [N][C][DH][DW] (albumentations A.Resize(256, 256) + ToTensorV2, utils/utils.py:318-323).
+ *      hd_sq_err_u8: sq_err[n] = sum (a - b)^2 per image (PSNR, utils/rotinas.py:21).
+ *      hd_uiqm_u8: out[n] = (UIQM, UICM, UISM, UIConM) of metrics/metrics.py:77-299 for [N][H][W][3] RGB images. ---- */
+int hd_resize_bilinear_u8(const void* src, int N, int SH, int SW, int C, void* dst, int DH, int DW, int chw, hd_stream_t stream);
+int hd_sq_err_u8(const void* a, const void* b, int N, int64_t per_image, double* sq_err, hd_stream_t stream);
+int64_t hd_uiqm_workspace(int N);
+int hd_uiqm_u8(const void* img, int N, int H, int W, void* workspace, int64_t ws_bytes, float* out, hd_stream_t stream);
+
 /* ---- GroupNorm(32) + Swish (+ Dropout): ModelCondition.py:128-129,141-143,95,249-250.  Two-source input
  *      (C0 | C1 channels) fuses torch.cat :271 into the normalisation.  sums/gsums = [N][G][2] fp64. ---- */
 int hd_gn_stats(int dtype, const void* in0, int C0, const void* in1, int C1, int N, int64_t HW, int G, double* sums,
