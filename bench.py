@@ -293,6 +293,57 @@ def gpu_reference(dev, res, steps=3):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def hybrid_leg(dev, res, ops, steps=5, batch=16):
+    """SURVEY 8(f) rank 2, the product's own model and settings (Main.py:16-35): DynamicUNet ch=128 ch_mult=[1,2,2,2] num_res_blocks=2
+    dropout=0.15, batch 16, 256x256 uint8 image pairs — one hybrid training step (trainer forward -> sum/1000 -> backward -> clip ->
+    AdamW) and the 100-step DDIM sampler.  Extra information next to the headline metric, not part of it."""
+    import torch
+    from hdiff_b200.diffusion.Model import DynamicUNet
+    from hdiff_b200.diffusion.Diffusion import GaussianDiffusionTrainer, GaussianDiffusionSampler
+    from hdiff_b200.optim import FlatAdamW
+    torch.manual_seed(0)
+    net = DynamicUNet(T=1000, ch=128, ch_mult=[1, 2, 2, 2], num_res_blocks=2, dropout=0.15).to(dev)
+    net.train()
+    tr = GaussianDiffusionTrainer(net, BETA_1, BETA_T, 1000).to(dev)
+    opt = FlatAdamW(net, lr=1e-4, weight_decay=1e-4, max_grad_norm=1.0)
+    g = torch.Generator(device=dev).manual_seed(1)
+    gt = [torch.randint(0, 256, (batch, 3, res, res), generator=g, device=dev, dtype=torch.uint8) for _ in range(3)]
+    inp = [torch.randint(0, 256, (batch, 3, res, res), generator=g, device=dev, dtype=torch.uint8) for _ in range(3)]
+    for k in range(3):
+        opt.zero_grad(); (tr(gt[k], inp[k], 0)[0].sum() / 1000.).backward(); opt.step()
+    torch.cuda.synchronize()
+    l0 = ops.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        opt.zero_grad()
+        loss = tr(gt[k % 3], inp[k % 3], 0)[0].sum() / 1000.
+        loss.backward()
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"model": "DynamicUNet ch=128 ch_mult=[1,2,2,2] num_res_blocks=2 dropout=0.15 (Main.py:16-35), 256x256, batch 16, uint8 pairs",
+           "params_m": sum(p.numel() for p in net.parameters()) / 1e6,
+           "train_images_per_s": batch / (ms * 1e-3), "train_ms_per_step": ms, "train_launches_per_step": (ops.launches - l0) / steps,
+           "train_loss": float(loss)}
+    del tr, opt
+    net.eval()
+    smp = GaussianDiffusionSampler(net, BETA_1, BETA_T, 1000).to(dev)
+    img = inp[0][:8].contiguous()
+    smp(img, ddim=True, unconditional_guidance_scale=1, ddim_step=4)        # warm-up: a 4-step chain (stride 250)
+    torch.cuda.synchronize()
+    e0.record()
+    y = smp(img, ddim=True, unconditional_guidance_scale=1, ddim_step=100)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    out.update({"ddim100_images_per_s": 8 / sec, "ddim100_chain_seconds": sec, "ddim_batch": 8, "ddim_out_abs_max": float(y.abs().max())})
+    del net, smp
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -472,6 +523,12 @@ def run_ours(args):
                     "launches": ops.launches - l1, "out_abs_max": float(x0.abs().max())}
         del snet, sampler, warm
         torch.cuda.empty_cache()
+    hybrid = None
+    if world == 1 and not args.no_hybrid:
+        try:
+            hybrid = hybrid_leg(dev, res, ops)
+        except Exception as e:                                              # noqa: BLE001
+            hybrid = {"unavailable": repr(e)[:300]}
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     gpu_ref = None
@@ -499,7 +556,7 @@ def run_ours(args):
                    "ms_per_step": ms_e2e / args.steps},
            "gpu_launches": launches, "tcgen05_launches_total": ops.tc_launches, "loss": loss_val,
            "step_algorithmic_tflops": step_tflops, "step_frac_of_sustained_bf16": step_tflops / peaks["bf16_tflops_sustained"],
-           "roofline": roof, "kernel_families": fam_out, "clocks": clk, "sampling": sampling, "gpu_reference": gpu_ref}
+           "roofline": roof, "kernel_families": fam_out, "clocks": clk, "sampling": sampling, "gpu_reference": gpu_ref, "hybrid": hybrid}
     if world == 1 and not args.no_cpu_baseline:
         v, sec, threads, kind = cpu_reference_steps(args.cpu_steps, 1, res, args.ref_batch, cond=cond)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
@@ -532,6 +589,7 @@ def main():
     ap.add_argument("--cpu-sample-steps", type=int, default=4, help="CFG sampler steps of the CPU baseline (0: skip)")
     ap.add_argument("--profile-steps", type=int, default=3, help="steps of the separate per-launch profiling pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hybrid", action="store_true", help="skip the DynamicUNet / hybrid pipeline leg")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--sample-steps", type=int, default=1000, help="length of the CFG sampling chain timed after training (0: skip)")
     ap.add_argument("--sample-batch", type=int, default=8, help="per-GPU sampling batch (configs[3]: 64 images over 8 GPUs)")
