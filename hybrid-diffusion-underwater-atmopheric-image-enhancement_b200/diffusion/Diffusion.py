@@ -6,7 +6,7 @@
     `forward(input_image, ddim, unconditional_guidance_scale, ddim_step)` around `DynamicUNet`.
 
 `GaussianDiffusionTrainer` / `GaussianDiffusionSampler` here serve both callers: the hybrid signature is recognised by its
-second positional argument (`input_image`) / by an image-conditioned model; `HybridGaussianDiffusion*` name it explicitly."""
+second positional argument (an image `input_image`, not a 1-d label vector) / by an image-conditioned model; `HybridGaussianDiffusion*` name it explicitly."""
 from ..diffusion_process import extract  # noqa: F401
 from ..diffusion_process import GaussianDiffusionSampler as _PlainSampler
 from ..hybrid_process import HybridGaussianDiffusionTrainer, HybridGaussianDiffusionSampler
@@ -14,8 +14,10 @@ from ..hybrid_process import HybridGaussianDiffusionTrainer, HybridGaussianDiffu
 
 class GaussianDiffusionTrainer(HybridGaussianDiffusionTrainer):
     def forward(self, x_0, input_image=None, stage=0):
-        if input_image is None:
-            return super(HybridGaussianDiffusionTrainer, self).forward(x_0)          # the plain trainer: forward(x_0) -> loss
+        # forward(x_0) / forward(x_0, labels[B] int): the plain / label-conditioned trainer; forward(gt_images, input_image[B,3,H,W],
+        # stage): the hybrid one
+        if input_image is None or (hasattr(input_image, "dim") and input_image.dim() == 1):
+            return super(HybridGaussianDiffusionTrainer, self).forward(x_0, input_image)
         return HybridGaussianDiffusionTrainer.forward(self, x_0, input_image, stage)
 
 

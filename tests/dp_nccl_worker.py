@@ -3,6 +3,11 @@ the CONDITIONAL UNet with label dropout on the CUDA kernels over NCCL against th
 batch (BASELINE.json configs[2]; reference step DiffusionFreeGuidence/TrainCondition.py:53-63, DDP wrap utils/rotinas.py:618-619).
     mode hdiff : hdiff_b200.parallel.enable_data_parallel (bucketed all-reduce issued from inside backward)
     mode ddp   : torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank])  — the reference's own wrap
+Second argument: fp32 (check mode: the exchange logic must reproduce the single-GPU gradients to 1e-4) or bf16 (product path).
+bf16 tolerance: two bf16 evaluations of this network that are not bit-identical (here: the fp32 partial sums of the GroupNorm
+statistics are formed over other tile ranges when the batch per GPU is 2 instead of 4) differ by about 1 % in their weight
+gradients — each is about 2 % from the fp32 oracle (scripts/debug_dp_split.py measures the same 1 % between a batch of 4 and the
+sum of its halves on ONE GPU, no communication involved) — so bf16 is held to 4e-2, the bound of the whole-network tests.
 Exit code 0 = every check passed on this rank."""
 import os
 import sys
@@ -16,6 +21,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     mode = sys.argv[1]
+    fp32 = len(sys.argv) > 2 and sys.argv[2] == "fp32"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -27,7 +33,8 @@ def main():
     cfg = dict(T=1000, ch=64, ch_mult=[1, 2, 2], attn=[1], num_res_blocks=1, dropout=0.0)
     res, b = 64, 2
     torch.manual_seed(100 + rank)                          # replicas start different: the wrap must broadcast rank 0's
-    net = UNet(num_labels=10, **cfg).to(dev).train()
+    cdt = torch.float32 if fp32 else torch.bfloat16
+    net = UNet(num_labels=10, compute_dtype=cdt, **cfg).to(dev).train()
     if mode == "hdiff":
         parallel.enable_data_parallel(net, bucket_bytes=1 << 20)      # small buckets: several overlapped collectives
         model = net
@@ -43,19 +50,19 @@ def main():
     before = hops.get().tc_launches
     loss = (model(x[sl], t[sl], lab[sl]) ** 2).sum() / b ** 2.
     loss.backward()
-    assert hops.get().tc_launches > before, "the tcgen05 kernels must run"
+    assert fp32 or hops.get().tc_launches > before, "the tcgen05 kernels must run"
     got = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
     if mode == "hdiff":
         assert net.last_reducer.launched >= 4, net.last_reducer.launched
     # single-GPU reference on the concatenated batch, same weights, no process group
-    ref = UNet(num_labels=10, **cfg).to(dev).train()
+    ref = UNet(num_labels=10, compute_dtype=cdt, **cfg).to(dev).train()
     ref.load_state_dict(net.state_dict())
     ((ref(x, t, lab) ** 2).sum() / b ** 2. / world).backward()
     gscale = max(float(p.grad.norm()) for p in ref.parameters())
     bad = []
     for k, p in ref.named_parameters():
         d = float((got[k] - p.grad).norm())
-        if d > 5e-3 * float(p.grad.norm()) + 1e-4 * gscale:
+        if d > (2e-4 if fp32 else 4e-2) * float(p.grad.norm()) + (1e-5 if fp32 else 2e-3) * gscale:
             bad.append((k, d / (float(p.grad.norm()) + 1e-30)))
     assert not bad, (rank, bad[:6])
     # one optimizer step keeps the replicas identical
@@ -68,7 +75,7 @@ def main():
     assert all(torch.equal(c, all_chk[0]) for c in all_chk), "replicas diverged after the step"
     dist.barrier()
     dist.destroy_process_group()
-    print(f"rank {rank} ok ({mode})", flush=True)
+    print(f"rank {rank} ok ({mode} {'fp32' if fp32 else 'bf16'})", flush=True)
 
 
 if __name__ == "__main__":

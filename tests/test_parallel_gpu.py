@@ -21,12 +21,13 @@ def _free_port():
     return port
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("mode", ["hdiff", "ddp"])
-def test_two_rank_nccl_gradients_match_single_gpu(mode):
+def test_two_rank_nccl_gradients_match_single_gpu(mode, dtype):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dp_nccl_worker.py"), mode]
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dp_nccl_worker.py"), mode, dtype]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" ok (") == 2, r.stdout[-2000:]
