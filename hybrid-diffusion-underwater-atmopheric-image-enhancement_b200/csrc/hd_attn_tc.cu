@@ -338,17 +338,42 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __nv_bfloa
             tmem_ld32(lane_base + kF2S, v);
             tmem_ld32(lane_base + kF2S + 32, v + 32);
             tmem_wait_ld();
-            float mx = __uint_as_float(v[0]);
+            // row maximum by four independent chains (one serial chain of 32 FMNMX3 was ~150 cycles on the critical path of a tile)
+            auto row_max = [&]() {
+                float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
-            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-            mx *= sl2;
+                for (int i = 4; i < 64; i += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(v[i])); m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(v[i + 2])); m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+                }
+                return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * sl2;
+            };
+            uint32_t pk[32];
+            float lsum;
+            auto exps = [&]() {                       // P = exp2(S * scale - m_ref), its row sum
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float a = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sl2, -m_ref));
+                    const float b = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_ref));
+                    s0 += a; s1 += b;
+                    pk[i] = pack_bf16x2(a, b);
+                }
+                lsum = s0 + s1;
+            };
             if (j == 0) {
-                m_ref = mx;
+                m_ref = row_max();
+                exps();
             } else {
+                // The reference maximum only moves when a tile exceeds it by more than the rescale threshold (rare after the first
+                // tiles), so the exponentials are formed SPECULATIVELY against the current one while the maximum of this tile is
+                // reduced beside them (MUFU and ALU pipes in parallel); a row that does grow recomputes them from its scores.
+                exps();
+                const float mx = row_max();
                 const bool grow_m = mx > m_ref + kRescaleThreshold;
                 if (__any_sync(0xffffffffu, grow_m)) {
                     float alpha = 1.f;
-                    if (grow_m) { alpha = fast_exp2(m_ref - mx); m_ref = mx; l *= alpha; }
+                    if (grow_m) { alpha = fast_exp2(m_ref - mx); m_ref = mx; l *= alpha; exps(); }
                     // O is at rest: S_j completed, and P_{j-1} V was issued before S_j on the in-order tensor pipe
 #pragma unroll 1
                     for (int c = 0; c < D; c += 32) {
@@ -362,14 +387,7 @@ attn_fwd2_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __nv_bfloa
                     tmem_wait_st();
                 }
             }
-            uint32_t pk[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float a = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sl2, -m_ref));
-                const float b = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_ref));
-                l += a + b;
-                pk[i] = pack_bf16x2(a, b);
-            }
+            l += lsum;
             tmem_st32(lane_base + kF2S, pk);          // in place: all 64 score columns of this row are in registers
             tmem_wait_st();
             tc_fence_before();
