@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhdiff_b200.so")
+LIB_PATH = os.environ.get("HDIFF_LIB_PATH") or os.path.join(HERE, "libhdiff_b200.so")      # (HDIFF_LIB_PATH: the lab build, for timing experiments)
 
 P, I, L, F, U64, D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_double
 

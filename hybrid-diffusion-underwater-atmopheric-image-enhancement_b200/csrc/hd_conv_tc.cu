@@ -45,6 +45,17 @@ __device__ long long g_conv_dbg[4];
 #define HD_CONV_DBG(p) 0
 #endif
 
+// residual add on the packed output: out = bf16(bf16(acc + bias + emb) + res), one HADD2.BF16 per pair instead of two unpacks and two
+// fp32 adds (the epilogue of a K = 576 tile is as long as its main loop, and the residual doubled its instruction count: 64->64
+// + residual 0.27 ms against 0.19 ms without).  The intermediate rounding is what h + shortcut(x) does in any bf16 evaluation of
+// the reference module (ModelCondition.py:161: conv output, then the add).
+__device__ __forceinline__ void add_res_bf16x8(uint4& o, const uint4& r) {
+    __nv_bfloat162* a = reinterpret_cast<__nv_bfloat162*>(&o);
+    const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = __hadd2(a[i], b[i]);
+}
+
 struct ConvTcParams {
     int N, H, W, TH, TW, tiles_x, tiles_y, m_tiles, n_tiles, NT;
     int k, pad, P_in, nchunk0, nchunk_c, kblocks, stages;
@@ -292,7 +303,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_arrive_expect_tx(&res_full[buf], kABytes);
             tma_load_5d(stage_buf + buf * kABytes, &mapRes, &res_full[buf], j0 - py * cv_w, txi * p.TW, py, tyi * p.TH, nn);
         };
-        if (kRes && p.stage_out && etid == 0 && t_begin < t_end) res_load(t_begin, 0, 0);
+        // The residual loads are issued by lane 0 of the SECOND epilogue warp: one thread needs ~300 cycles to issue a tensor copy, and
+        // thread 0 already issues the tile's tensor store (ncu: with both on thread 0 the other seven warps sat 11 % of their samples
+        // at the next tile's barrier; 64->64 + residual 291 us against 199 us without one)
+        constexpr int kResIssuer = 32;
+        const bool early_res = kRes && p.stage_out && p.NT == 64;
+        if (kRes && p.stage_out && etid == kResIssuer && t_begin < t_end) res_load(t_begin, 0, 0);
         // staged epilogue + statistics (Cout == 64: one block per tile): per-channel (sum, sum of squares) of the STORED bf16
         // values are read back out of the staged tile; every warp keeps the sums of its 16 pixel rows in registers (lane:
         // channels 2 lane, 2 lane + 1) across this CTA's consecutive tiles of one image and adds them to p.chan_sums (fp64
@@ -363,6 +379,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     pre_b[0] = __ldg(rq); pre_b[1] = __ldg(rq + 1);
                 }
             }
+            if (early_res && has_next && etid == 0) {
+                // one block per tile: the other staging buffer held tile i-1's output, whose store was issued a whole tile ago.
+                // Requesting tile i+1's residual NOW (not after this tile's store) puts it a full epilogue earlier into the TMA
+                // queue, which the four producer threads keep ~3 operand stages deep.
+                bulk_wait_group_read0();
+                res_load(tile + t_step, 0, (sb + 1) & 1);
+            }
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
             if (HD_CONV_DBG(p) & 1) {
@@ -409,20 +432,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         f[4 * i] = __uint_as_float(v[4 * i]) + a.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + a.y;
                         f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + a.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + a.w;
                     }
-                    if (kRes) {          // the residual block sits (swizzled) where the output is about to be written
-                        const uint4 r0 = *reinterpret_cast<const uint4*>(srow + ((cb ^ (row & 7)) << 4));
-                        const uint4 r1 = *reinterpret_cast<const uint4*>(srow + (((cb + 1) ^ (row & 7)) << 4));
-                        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-                        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float2 a = __bfloat1622float2(h0[i]), b = __bfloat1622float2(h1[i]);
-                            f[2 * i] += a.x; f[2 * i + 1] += a.y; f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
-                        }
-                    }
                     uint4 o0, o1;
                     o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
                     o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                    if (kRes) {          // the residual block sits (swizzled) where the output is about to be written
+                        const uint4 r0 = *reinterpret_cast<const uint4*>(srow + ((cb ^ (row & 7)) << 4));
+                        const uint4 r1 = *reinterpret_cast<const uint4*>(srow + (((cb + 1) ^ (row & 7)) << 4));
+                        add_res_bf16x8(o0, r0); add_res_bf16x8(o1, r1);
+                    }
                     *reinterpret_cast<uint4*>(srow + ((cb ^ (row & 7)) << 4)) = o0;             // 128-byte swizzle: chunk ^= row % 8
                     *reinterpret_cast<uint4*>(srow + (((cb + 1) ^ (row & 7)) << 4)) = o1;
                 };
@@ -463,10 +480,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         const int py = j0 / cv_w;
                         tma_store_5d(&mapOut, sbuf, j0 - py * cv_w, tx_i * p.TW, py, ty_i * p.TH, n);
                         bulk_commit_group();
-                        if (kRes) {      // the other buffer is free (its store was read out before the barrier): fetch the next block
-                            if (c + 64 < p.NT) res_load(tile, (c - half * 16) / 64 + 1, (sb + 1) & 1);
-                            else if (has_next) res_load(tile + t_step, 0, (sb + 1) & 1);
-                        }
+                    }
+                    if (kRes && etid == kResIssuer) {      // the other buffer is free (thread 0 saw its store read out before it joined the
+                                                           // barrier above): fetch the next residual block
+                        if (c + 64 < p.NT) res_load(tile, (c - half * 16) / 64 + 1, (sb + 1) & 1);
+                        else if (has_next && !early_res) res_load(tile + t_step, 0, (sb + 1) & 1);
                     }
                     if (sstat) {         // this warp: 16 of the 128 staged pixel rows; lane: channels 2 lane, 2 lane + 1 of the block
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f, s2 = 0.f, s3 = 0.f, q2 = 0.f, q3 = 0.f;
@@ -509,21 +527,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         f[4 * i] = __uint_as_float(v[4 * i]) + a.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + a.y;
                         f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + a.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + a.w;
                     }
+                    uint4 o0, o1;
+                    o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+                    o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
                     if (kRes) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
                         uint4 r0, r1;
                         if (pre) { r0 = pre[0]; r1 = pre[1]; } else { r0 = __ldg(rp); r1 = __ldg(rp + 1); }
-                        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-                        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float2 a = __bfloat1622float2(h0[i]), b = __bfloat1622float2(h1[i]);
-                            f[2 * i] += a.x; f[2 * i + 1] += a.y; f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
-                        }
+                        add_res_bf16x8(o0, r0); add_res_bf16x8(o1, r1);
                     }
-                    uint4 o0, o1;
-                    o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]); o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
-                    o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]); o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
                     uint4* op = reinterpret_cast<uint4*>(p.out + off);
                     op[0] = o0; op[1] = o1;
                     // the values as stored (bf16), for the statistics
@@ -626,7 +638,7 @@ bool conv_geometry(int H, int W, int* TH, int* TW) {
 
 // Shared-memory plan and kernel modes of a launch (p.N .. p.kblocks, p.NT, p.kb_w already set).  Returns false when nothing fits.
 static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out, int ksize, int out_nchw_c, bool chan_sums,
-                      bool allow_stage) {
+                      bool allow_stage, bool has_res = false) {
     (void)P_out;
     // Shared-memory plan.  Options, each dropped when the ring would get too short:
         //   txm   shifted-operand mode: 3x3, a tile is one 128-pixel row segment (needs >= 3 stages)
@@ -670,6 +682,9 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
         static const int mma2_env = getenv("HDIFF_CONV_MMA2") ? atoi(getenv("HDIFF_CONV_MMA2")) : -1;
         int mode = 0;                                   // by shape, from per-layer timings inside a training step
         if (p.NT <= 64) mode = ksize == 1 ? 1 : 2;
+        // K = 576 tiles WITH a residual are bound by their epilogue (lab build: MMA stream alone 0.142 ms, + epilogue 0.196, + residual
+        // 0.262 at 64->64 @256^2); there the partial accumulators of mode 2 only add epilogue work: one issuer 0.247 ms
+        if (p.NT <= 64 && ksize == 3 && has_res && p.nchunk_c * P_in <= 1) mode = 0;
         else if (p.NT <= 128 && ksize == 3) mode = (p.txm && P_in == 1) ? 0 : 2;
         p.mma2 = mma2_env >= 0 ? mma2_env : mode;
         if (p.mma2 == 2 && (p.NT > 128 || p.wres)) p.mma2 = p.NT <= 64 ? 1 : 0;
@@ -756,7 +771,7 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     p.kb_w = p.kblocks;
     // statistics in the staged epilogue handle one 64-channel block per tile; other widths with `chan_sums` take the direct-store
     // epilogue and its register butterfly
-    HD_REQUIRE(conv_plan(p, CoutL, Cout, P_in, P_out, ksize, out_nchw_c, chan_sums != nullptr, !chan_sums || Cout == 64));
+    HD_REQUIRE(conv_plan(p, CoutL, Cout, P_in, P_out, ksize, out_nchw_c, chan_sums != nullptr, !chan_sums || Cout == 64, res != nullptr));
     const int stage_bytes = p.a_slot + (p.wres ? 0 : (p.txm ? 3 : 1) * p.NT * 128);
     p.nprod = p.stages < kProducers ? p.stages : kProducers;
     p.Cout = Cout; p.P_out = P_out;

@@ -6,7 +6,8 @@ import sys
 
 WANT = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
-        ("sm__pipe_tensor_subpipe_umma_cycles_active.avg.pct_of_peak_sustained_elapsed", "umma%"),
+        ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor%"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
         ("sm__inst_executed_pipe_uniform", "uni"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
         ("lts__t_bytes.sum", "l2_bytes"),
@@ -24,7 +25,8 @@ for rep in sys.argv[1:]:
     for row in rows[2:]:
         parts = [row[hdr.index("Kernel Name")][:48]]
         for key, short in WANT:
-            if key in hdr:
-                i = hdr.index(key)
+            cols = [i for i, h in enumerate(hdr) if h == key or h.endswith("." + key)]      # some columns carry a section prefix
+            if cols:
+                i = cols[0]
                 parts.append(f"{short}={row[i]}{units[i]}")
         print("  ".join(parts))
