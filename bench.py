@@ -333,12 +333,16 @@ def hybrid_leg(dev, res, ops, steps=5, batch=16):
     img = inp[0][:8].contiguous()
     smp(img, ddim=True, unconditional_guidance_scale=1, ddim_step=4)        # warm-up: a 4-step chain (stride 250)
     torch.cuda.synchronize()
-    e0.record()
-    y = smp(img, ddim=True, unconditional_guidance_scale=1, ddim_step=100)
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3
-    out.update({"ddim100_images_per_s": 8 / sec, "ddim100_chain_seconds": sec, "ddim_batch": 8, "ddim_out_abs_max": float(y.abs().max())})
+    secs = []
+    for _ in range(2):                      # the public call captures its step graph every time (host-side cost: 0.1-0.8 s on these boxes)
+        e0.record()
+        y = smp(img, ddim=True, unconditional_guidance_scale=1, ddim_step=100)
+        e1.record()
+        torch.cuda.synchronize()
+        secs.append(e0.elapsed_time(e1) * 1e-3)
+    sec = min(secs)
+    out.update({"ddim100_images_per_s": 8 / sec, "ddim100_chain_seconds": sec, "ddim100_chain_seconds_each_call": secs, "ddim_batch": 8,
+                "ddim_out_abs_max": float(y.abs().max())})
     del net, smp
     torch.cuda.empty_cache()
     return out
