@@ -167,7 +167,8 @@ def test_head_tail_layout_convs():
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1e-2)])
-@pytest.mark.parametrize("shape", [(2, 16 * 16, 64, 0), (2, 8 * 8, 128, 64), (1, 32 * 32, 192, 0), (3, 100, 32, 0)])
+@pytest.mark.parametrize("shape", [(2, 16 * 16, 64, 0), (2, 8 * 8, 128, 64), (1, 32 * 32, 192, 0), (3, 100, 32, 0),
+                                   (2, 16 * 16, 512, 512), (3, 777, 256, 0), (5, 7, 64, 32)])
 def test_groupnorm_swish_forward_backward(dtype, tol, shape):
     N, HW, C0, C1 = shape
     dev = torch.device("cuda")
