@@ -6,7 +6,7 @@ batch (BASELINE.json configs[2]; reference step DiffusionFreeGuidence/TrainCondi
 Second argument: fp32 (check mode: the exchange logic must reproduce the single-GPU gradients to 1e-4) or bf16 (product path).
 bf16 tolerance: two bf16 evaluations of this network that are not bit-identical (here: the fp32 partial sums of the GroupNorm
 statistics are formed over other tile ranges when the batch per GPU is 2 instead of 4) differ by about 1 % in their weight
-gradients — each is about 2 % from the fp32 oracle (scripts/debug_dp_split.py measures the same 1 % between a batch of 4 and the
+gradients — each is about 2 % from the fp32 oracle (tests/tools/debug_dp_split.py measures the same 1 % between a batch of 4 and the
 sum of its halves on ONE GPU, no communication involved) — so bf16 is held to 4e-2, the bound of the whole-network tests.
 Exit code 0 = every check passed on this rank."""
 import os

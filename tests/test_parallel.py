@@ -141,3 +141,64 @@ def test_stock_distributed_data_parallel_wrap(cond):
     assert abs(res[0][2] - res[1][2]) < 1e-6, "DDP did not broadcast rank 0's parameters into the flat buffer"
     for rank, worst, _ in res:
         assert worst < 2e-4, (rank, worst)
+
+
+def _worker_dynamic(rank, world, port, q, context_zero):
+    """DynamicUNet under hdiff_b200's data parallelism.  With the image condition encoder in use its convolutions are the LAST
+    weight gradients of a backward pass (engine: `late_conv`): the exchange of the packed buffer must wait for them.  The gate
+    freezes every other middle block: those parameters must end without a gradient on every rank."""
+    import hdiff_b200.ops as hops
+    from hdiff_b200 import parallel
+    from hdiff_b200.diffusion.Model import DynamicUNet
+    from tests.emu_backend import EmuOps
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    hops.set_backend(EmuOps())
+    cfg = dict(T=50, ch=32, ch_mult=[1, 2], num_res_blocks=1, dropout=0.0)
+    torch.manual_seed(55 + rank)
+    net = DynamicUNet(compute_dtype=torch.float32, **cfg)
+    with torch.no_grad():
+        net.tail[-1].weight.mul_(3e4)
+    parallel.enable_data_parallel(net, bucket_bytes=64 << 10)
+    torch.manual_seed(8)
+    x = torch.randn(4, 6, 16, 16)
+    x[:, 2] += 1.0                                  # every shard "subaquatic": the same gate decision on both ranks
+    t = torch.tensor([3, 9, 20, 41])
+    lab = torch.randn(4, 3, 16, 16)
+    gy = torch.randn(4, 3, 16, 16)
+    sl = slice(rank * 2, rank * 2 + 2)
+    net(x[sl], t[sl], lab[sl], context_zero=context_zero).backward(gy[sl])
+    got = {k: (None if p.grad is None else p.grad.clone()) for k, p in net.named_parameters()}
+    ref = DynamicUNet(compute_dtype=torch.float32, **cfg)
+    ref.load_state_dict(net.state_dict())
+    ref(x, t, lab, context_zero=context_zero).backward(gy)
+    worst, gmax = 0.0, max(float(p.grad.norm()) for p in ref.parameters() if p.grad is not None)
+    for k, p in ref.named_parameters():
+        if p.grad is None:
+            assert got[k] is None, k
+            continue
+        d = float((got[k] - p.grad / world).norm())
+        worst = max(worst, d / (float(p.grad.norm()) / world + 1e-5 * gmax))
+    q.put((rank, worst, net.last_reducer.launched))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("context_zero", [True, False], ids=["context_zero", "image_condition"])
+def test_dynamic_unet_two_rank_gradient_mean(context_zero):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_dynamic, args=(r, world, port, q, context_zero)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, worst, n_coll in res:
+        assert worst < 3e-4, (rank, worst)
+        assert n_coll >= 3

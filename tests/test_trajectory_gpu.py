@@ -162,7 +162,7 @@ def test_fixed_noise_1000_step_cfg_sampling_psnr_on_a_trained_network():
     # ---- train the ORACLE for a few hundred steps on smooth synthetic images (class = colour cast), copy the weights ----
     ref.train()
     rtr = R.GaussianDiffusionTrainer(ref, 1e-4, 0.02, 1000).to(dev)
-    # recipe found with scripts/explore_saturation.py: 400 steps on +-0.9 images leave 73 % of the sampled pixels clipped,
+    # recipe found with tests/tools/explore_saturation.py: 400 steps on +-0.9 images leave 73 % of the sampled pixels clipped,
     # 1500 steps at lr 3e-4 on +-0.5 images leave 33 %
     ropt = torch.optim.AdamW(ref.parameters(), lr=3e-4, weight_decay=1e-4)
     g = torch.Generator(device="cuda").manual_seed(5)

@@ -2,7 +2,7 @@
 against the fp32 oracle: which side of tests/dp_nccl_worker.py's comparison is off?"""
 import os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from hdiff_b200.DiffusionFreeGuidence.ModelCondition import UNet
 from oracle import ref_torch as R
