@@ -28,7 +28,7 @@ def timeit(name, fn, work, unit):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(f"{name:44s} {ms:8.3f} ms   {work / ms / 1e9:9.1f} {unit}", flush=True)
+    print(f"{name:44s} {ms:8.3f} ms   {work / ms / 1e6:9.1f} {unit}", flush=True)
 
 
 if what in ("conv", "wgrad", "all"):
@@ -103,4 +103,24 @@ if what in ("gn", "all"):
         tot = torch.zeros(C, device=dev)
         timeit(f"colsum N{N} HW{HW} C{C}", lambda: ops.colsum(t, N, HW, C, pn, tot), numel * 2.0, "GB/s")
         del x0, x1, out, dy, dx0, dx1, t
+if what in ("mha", "all"):
+    # the 8-head attention core at DynamicUNet's middle blocks (product configuration: 32x32, C = 256 -> hd = 32, batch 16) and at the
+    # live ModelCondition UNet's CIFAR-sized levels (32x32 C = 128 -> hd = 16; 16x16 C = 256)
+    for (N, S, C) in ((16, 1024, 256), (32, 1024, 128), (32, 256, 256), (8, 4096, 64)):
+        qkv = torch.randn(N, S, 3 * C, device=dev).to(bf)
+        out = torch.empty(N, S, C, dtype=bf, device=dev)
+        dout = torch.randn(N, S, C, device=dev).to(bf)
+        dqkv = torch.empty_like(qkv)
+        lse = torch.empty(N, 8, S, device=dev)
+        delta = torch.empty(N, 8, S, device=dev)
+        timeit(f"mha fwd N{N} S{S} C{C} (8 heads)", lambda: ops.mha_fwd(qkv, out, lse, N, S, C, 8), 4.0 * N * S * S * C / 1e3, "TFLOP/s")
+        timeit(f"mha bwd N{N} S{S} C{C} (8 heads)", lambda: ops.mha_bwd(qkv, out, dout, lse, delta, dqkv, N, S, C, 8), 8.0 * N * S * S * C / 1e3, "TFLOP/s")
+
+if what in ("metrics", "all"):
+    from hdiff_b200 import metrics
+    src = torch.randint(0, 256, (64, 720, 1280, 3), device=dev, dtype=torch.uint8)
+    timeit("resize_u8 64 x 720x1280 -> 256x256 (CHW)", lambda: metrics.resize_u8(src, 256, 256), (src.numel() + 64 * 3 * 256 * 256) * 1.0, "GB/s")
+    img = torch.randint(0, 256, (64, 256, 256, 3), device=dev, dtype=torch.uint8)
+    timeit("uiqm_u8 64 x 256x256", lambda: metrics.uiqm_u8(img), img.numel() * 3.0, "GB/s")
+    timeit("psnr_u8 64 x 256x256", lambda: metrics.psnr_u8(img, img.flip(0).contiguous()), img.numel() * 2.0, "GB/s")
 print("done")
