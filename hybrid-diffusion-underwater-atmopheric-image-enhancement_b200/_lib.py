@@ -47,6 +47,8 @@ PROTOTYPES = {
     "hd_wgrad_tc_workspace": [I, I, I, I, I, I, I, I, I],
     "hd_attn_fwd_tc": [P, P, P, I, I, I, P],
     "hd_attn_bwd_tc": [P, P, P, P, P, P, I, I, I, P],
+    "hd_attn_fwd_tc_scaled": [P, P, P, I, I, F, P],
+    "hd_attn_bwd_tc_scaled": [P, P, P, P, P, P, I, I, F, P],
     "hd_attn_tc_supported": [I, I],
     "hd_attn_wide_tc_supported": [I, I],
     "hd_attn_fwd_wide_tc": [P, P, P, I, I, I, P],
@@ -60,6 +62,8 @@ PROTOTYPES = {
     "hd_uiqm_workspace": [I],
     "hd_uiqm_u8": [P, I, I, I, P, L, P, P],
     "hd_mha_supported": [I, I],
+    "hd_mha_pack_heads": [P, P, I, I, I, I, I, F, P],
+    "hd_mha_unpack_heads": [P, P, I, I, I, I, I, F, P],
     "hd_mha_fwd": [I, P, P, P, I, I, I, I, P],
     "hd_mha_bwd": [I, P, P, P, P, P, P, I, I, I, I, P],
 }

@@ -724,15 +724,28 @@ extern "C" int hd_attn_tc_supported(int S, int C) {
 }
 extern "C" int hd_attn_bwd_tc_supported(int S, int C) { return hd_attn_tc_supported(S, C); }
 
+extern "C" int hd_attn_fwd_tc_scaled(const void* qkv, void* out, float* lse, int N, int S, float scale, cudaStream_t stream);
+extern "C" int hd_attn_bwd_tc_scaled(const void* qkv, const void* out, const void* dout, const float* lse, float* stats, void* dqkv,
+                                     int N, int S, float scale, cudaStream_t stream);
+
 extern "C" int hd_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int S, int C, cudaStream_t stream) {
     HD_REQUIRE(qkv && out && lse && N > 0);
     if (!hd_attn_tc_supported(S, C)) { hd_set_error("hd_attn_fwd_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
     if (C != D) return hd_attn_fwd_wide_tc(qkv, out, lse, N, S, C, stream);
+    return hd_attn_fwd_tc_scaled(qkv, out, lse, N, S, 1.f / sqrtf((float)C), stream);
+}
+
+// The 128-channel kernel with the softmax scale given by the caller: softmax(q k^T * scale) v.  The multi-head route (hd_mha.cu)
+// runs zero-padded heads of dim hd here with scale = hd^-1/2.
+extern "C" int hd_attn_fwd_tc_scaled(const void* qkv, void* out, float* lse, int N, int S, float scale, cudaStream_t stream) {
+    const int C = D;
+    HD_REQUIRE(qkv && out && lse && N > 0 && N <= 65535 && scale > 0.f);
+    if (!hd_attn_tc_supported(S, C)) { hd_set_error("hd_attn_fwd_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
     CUtensorMap m;
     int rc = make_qkv_map(&m, qkv, N, S, 3 * C, 64); if (rc) return rc;
     AttnFwdParams p{};
     p.N = N; p.S = S; p.tiles = S / BN;
-    p.scale_log2 = 1.4426950408889634f / sqrtf((float)C);
+    p.scale_log2 = 1.4426950408889634f * scale;
     p.out = (__nv_bfloat16*)out; p.lse = lse;
     const size_t smem = kQBytes + kStages * kStageBytes + 1024 + 16 * 8;
     static unsigned long long attr_set = 0;
@@ -763,6 +776,14 @@ extern "C" int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout
     HD_REQUIRE(qkv && out && dout && lse && stats && dqkv && N > 0);
     if (!hd_attn_bwd_tc_supported(S, C)) { hd_set_error("hd_attn_bwd_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
     if (C != D) return hd_attn_bwd_wide_tc(qkv, out, dout, lse, stats, dqkv, N, S, C, stream);
+    return hd_attn_bwd_tc_scaled(qkv, out, dout, lse, stats, dqkv, N, S, 1.f / sqrtf((float)C), stream);
+}
+
+extern "C" int hd_attn_bwd_tc_scaled(const void* qkv, const void* out, const void* dout, const float* lse, float* stats, void* dqkv,
+                                     int N, int S, float scale, cudaStream_t stream) {
+    const int C = D;
+    HD_REQUIRE(qkv && out && dout && lse && stats && dqkv && N > 0 && N <= 65535 && scale > 0.f);
+    if (!hd_attn_bwd_tc_supported(S, C)) { hd_set_error("hd_attn_bwd_tc: unsupported shape"); return HD_ERR_UNSUPPORTED; }
     CUtensorMap mQKV, mDO;
     int rc = make_qkv_map(&mQKV, qkv, N, S, 3 * C, 64); if (rc) return rc;
     rc = make_qkv_map(&mDO, dout, N, S, C, 64); if (rc) return rc;
@@ -771,7 +792,7 @@ extern "C" int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout
     HD_CHECK_LAUNCH();
     AttnBwdParams p{};
     p.N = N; p.S = S; p.tiles = S / BN;
-    p.scale = 1.f / sqrtf((float)C);
+    p.scale = scale;
     p.scale_log2 = 1.4426950408889634f * p.scale;
     p.stats = (const float2*)stats; p.dqkv = (__nv_bfloat16*)dqkv;
     p.qkv = (const __nv_bfloat16*)qkv; p.dout = (const __nv_bfloat16*)dout;

@@ -229,7 +229,79 @@ template <typename T> int mha_bwd_d(int hd, const void* qkv, const void* out, co
     MHA_DISPATCH(mha_bwd_t, qkv, out, dout, lse, delta, dqkv, N, S, C, heads, st)
 }
 
+// ---- head packing for the tensor-core route ---------------------------------------------------------------------------------
+// The tcgen05 attention kernels (hd_attn_tc.cu) are built for head dim 128.  For head dims 8-64 (multiples of 8) the heads are
+// zero-padded to 128 channels and run there as N * heads independent sequences: 2-16x the useful MMA work, still an order of
+// magnitude faster than the CUDA-core kernel above (hd = 32, S = 1024, 128 sequences: 0.11 vs 0.65 ms forward).  Zero channels
+// change neither the scores nor the outputs, and their gradients come out as zeros.
+//   pack   : src [N][S][parts * C] -> dst [N * heads][S][parts * 128], dst(n h, s, p, d) = d < hd ? src(n, s, p, h hd + d) * (p == 0 ? scale0 : 1) : 0
+//   unpack : the inverse for d < hd (same scale on part 0)
+// One thread per 16-byte chunk of a destination row.
+__global__ void mha_pack_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int S, int C, int heads, int hd,
+                                int parts, float scale0, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % 16);                         // chunk of 8 channels inside the padded head
+        int64_t r = i / 16;
+        const int p = (int)(r % parts); r /= parts;
+        const int s = (int)(r % S); r /= S;
+        const int h = (int)(r % heads);
+        const int64_t n = r / heads;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (j * 8 < hd) {
+            v = __ldg(reinterpret_cast<const uint4*>(src + ((n * S + s) * (int64_t)parts + p) * C + h * hd + j * 8));
+            if (p == 0 && scale0 != 1.f) {
+                __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(q[k]); q[k] = __floats2bfloat162_rn(f.x * scale0, f.y * scale0); }
+            }
+        }
+        reinterpret_cast<uint4*>(dst)[i] = v;
+    }
+}
+__global__ void mha_unpack_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int S, int C, int heads, int hd,
+                                  int parts, float scale0, int64_t total) {
+    const int cph = hd / 8;                                  // chunks per head
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % cph);
+        int64_t r = i / cph;
+        const int h = (int)(r % heads); r /= heads;
+        const int p = (int)(r % parts); r /= parts;
+        const int s = (int)(r % S);
+        const int64_t n = r / S;
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (((n * heads + h) * S + s) * (int64_t)parts + p) * 128 + j * 8));
+        if (p == 0 && scale0 != 1.f) {
+            __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(q[k]); q[k] = __floats2bfloat162_rn(f.x * scale0, f.y * scale0); }
+        }
+        *reinterpret_cast<uint4*>(dst + ((n * S + s) * (int64_t)parts + p) * C + h * hd + j * 8) = v;
+    }
+}
+
 }  // namespace
+
+// bf16 only.  parts = 3 (q | k | v) or 1 (o, dO).  scale0 multiplies part 0 (1 in the product path: the softmax scale hd^-1/2 goes to
+// hd_attn_*_tc_scaled directly, so packing is exact).
+extern "C" int hd_mha_pack_heads(const void* src, void* dst, int N, int S, int C, int heads, int parts, float scale0, cudaStream_t stream) {
+    HD_REQUIRE(src && dst && N > 0 && S > 0 && heads > 0 && C % heads == 0 && (parts == 1 || parts == 3));
+    const int hd = C / heads;
+    HD_REQUIRE(hd % 8 == 0 && hd <= 128);
+    const int64_t total = (int64_t)N * heads * S * parts * 16;
+    int64_t blocks = (total + 255) / 256; if (blocks > (int64_t)hd_num_sms() * 16) blocks = (int64_t)hd_num_sms() * 16;
+    mha_pack_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, S, C, heads, hd, parts, scale0, total);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+extern "C" int hd_mha_unpack_heads(const void* src, void* dst, int N, int S, int C, int heads, int parts, float scale0, cudaStream_t stream) {
+    HD_REQUIRE(src && dst && N > 0 && S > 0 && heads > 0 && C % heads == 0 && (parts == 1 || parts == 3));
+    const int hd = C / heads;
+    HD_REQUIRE(hd % 8 == 0 && hd <= 128);
+    const int64_t total = (int64_t)N * S * parts * heads * (hd / 8);
+    int64_t blocks = (total + 255) / 256; if (blocks > (int64_t)hd_num_sms() * 16) blocks = (int64_t)hd_num_sms() * 16;
+    mha_unpack_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, S, C, heads, hd, parts, scale0, total);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
 
 extern "C" int hd_mha_supported(int C, int heads) {
     if (heads <= 0 || C % heads != 0) return 0;

@@ -38,6 +38,7 @@ class CudaOps:
         self.gn_inplace = __import__("os").environ.get("HDIFF_GN_INPLACE", "1") != "0"   # GroupNorm backward: the reduce pass hands dy' to the apply pass in place
         self.gn_fused = __import__("os").environ.get("HDIFF_GN_FUSED", "0") != "0"   # one cooperative launch per GroupNorm backward (measured slower: see DESIGN.md)
         self._gn_counter = None
+        self.mha_tc = __import__("os").environ.get("HDIFF_MHA_TC", "1") != "0"     # 8-head attention on the tcgen05 kernels (padded heads)
         self.prof = None            # bench.py: dict family -> [(start_event, end_event, work)], CUDA events on the launch stream
 
     # ---- per-launch device timing for bench.py's roofline (off unless `prof` is a dict) ----
@@ -153,15 +154,51 @@ class CudaOps:
         self.launches += 3
         self._t1(e0, "attn_bwd_tc" if tc else "attn_bwd_simt", 8.0 * N * S * S * C)
 
+    def _mha_tc(self, qkv, S, C, heads):
+        """Tensor-core route: head dims 8..64 run zero-padded on the 128-channel tcgen05 attention kernels (see csrc/hd_mha.cu)."""
+        hd = C // heads
+        return (self.use_tc and qkv.dtype == torch.bfloat16 and hd % 8 == 0 and hd <= 64 and self.mha_tc
+                and self.lib.hd_attn_tc_supported(S, 128) and self.lib.hd_attn_bwd_tc_supported(S, 128))
+
     def mha_fwd(self, qkv, out, lse, N, S, C, heads):
         """Multi-head self-attention core (nn.MultiheadAttention with q = k = v): qkv [N, S, 3C] -> out [N, S, C], lse [N, heads, S]."""
         e0 = self._t0()
+        if self._mha_tc(qkv, S, C, heads):
+            hd = C // heads
+            pad = torch.empty((N * heads, S, 3 * 128), dtype=qkv.dtype, device=qkv.device)
+            opad = torch.empty((N * heads, S, 128), dtype=qkv.dtype, device=qkv.device)
+            _lib.check(self.lib.hd_mha_pack_heads(_p(qkv), _p(pad), N, S, C, heads, 3, 1.0, _stream()), "hd_mha_pack_heads")
+            _lib.check(self.lib.hd_attn_fwd_tc_scaled(_p(pad), _p(opad), _p(lse), N * heads, S, hd ** -0.5, _stream()), "hd_attn_fwd_tc_scaled")
+            _lib.check(self.lib.hd_mha_unpack_heads(_p(opad), _p(out), N, S, C, heads, 1, 1.0, _stream()), "hd_mha_unpack_heads")
+            self.launches += 3
+            self.tc_launches += 1
+            self._t1(e0, "mha_fwd_tc", 4.0 * N * S * S * C)
+            return
         _lib.check(self.lib.hd_mha_fwd(_DT[qkv.dtype], _p(qkv), _p(out), _p(lse), N, S, C, heads, _stream()), "hd_mha_fwd")
         self.launches += 1
         self._t1(e0, "mha_fwd", 4.0 * N * S * S * C)
 
     def mha_bwd(self, qkv, out, dout, lse, delta, dqkv, N, S, C, heads):
         e0 = self._t0()
+        if self._mha_tc(qkv, S, C, heads):
+            hd = C // heads
+            dev, dt = qkv.device, qkv.dtype
+            pad = torch.empty((N * heads, S, 3 * 128), dtype=dt, device=dev)
+            opad = torch.empty((N * heads, S, 128), dtype=dt, device=dev)
+            gpad = torch.empty((N * heads, S, 128), dtype=dt, device=dev)
+            dpad = torch.empty((N * heads, S, 3 * 128), dtype=dt, device=dev)
+            stats = torch.empty((N * heads, S, 2), dtype=torch.float32, device=dev)
+            lib, st = self.lib, _stream()
+            _lib.check(lib.hd_mha_pack_heads(_p(qkv), _p(pad), N, S, C, heads, 3, 1.0, st), "hd_mha_pack_heads")
+            _lib.check(lib.hd_mha_pack_heads(_p(out), _p(opad), N, S, C, heads, 1, 1.0, st), "hd_mha_pack_heads")
+            _lib.check(lib.hd_mha_pack_heads(_p(dout), _p(gpad), N, S, C, heads, 1, 1.0, st), "hd_mha_pack_heads")
+            _lib.check(lib.hd_attn_bwd_tc_scaled(_p(pad), _p(opad), _p(gpad), _p(lse), _p(stats), _p(dpad), N * heads, S, hd ** -0.5, st),
+                       "hd_attn_bwd_tc_scaled")
+            _lib.check(lib.hd_mha_unpack_heads(_p(dpad), _p(dqkv), N, S, C, heads, 3, 1.0, st), "hd_mha_unpack_heads")
+            self.launches += 7
+            self.tc_launches += 2
+            self._t1(e0, "mha_bwd_tc", 8.0 * N * S * S * C)
+            return
         _lib.check(self.lib.hd_mha_bwd(_DT[qkv.dtype], _p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), N, S, C, heads, _stream()),
                    "hd_mha_bwd")
         self.launches += 2

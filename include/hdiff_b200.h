@@ -70,6 +70,10 @@ int hd_attn_fwd_tc(const void* qkv, void* out, float* lse, int N, int S, int C, 
  * atomics; `stats` is caller-provided scratch of N*S*2 floats ((lse*log2e, rowsum(dout*out)) per row). */
 int hd_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, float* stats, void* dqkv,
                    int N, int S, int C, hd_stream_t stream);
+/* the 128-channel kernels with the softmax scale supplied (softmax(q k^T * scale) v); used by the multi-head route */
+int hd_attn_fwd_tc_scaled(const void* qkv, void* out, float* lse, int N, int S, float scale, hd_stream_t stream);
+int hd_attn_bwd_tc_scaled(const void* qkv, const void* out, const void* dout, const float* lse, float* stats, void* dqkv,
+                          int N, int S, float scale, hd_stream_t stream);
 /* Wide heads (C a multiple of 128 up to 1024; hd_attn_*_tc forward to these when C != 128): the AttnBlocks of the wider
  * UNet of BASELINE.json configs[4] (C = 256 at 64x64, C = 512 at 32x32).  Same arguments and semantics as above. */
 int hd_attn_wide_tc_supported(int S, int C);
@@ -82,6 +86,10 @@ int hd_attn_bwd_wide_tc(const void* qkv, const void* out, const void* dout, cons
  *      qkv [N][S][3C] is the packed in-projection's output (q | k | v, head h = channels [h*C/heads, (h+1)*C/heads) of each);
  *      out / dout [N][S][C]; lse / delta [N][heads][S] fp32 (delta is scratch).  Head dims 4, 8, 16, 32, 64. ---- */
 int hd_mha_supported(int C, int heads);
+/* tensor-core route for head dims 8..64 (bf16): heads zero-padded to the 128-channel layout of hd_attn_*_tc, N * heads sequences.
+ * pack: src [N][S][parts*C] -> dst [N*heads][S][parts*128]; unpack: the inverse; parts = 3 (q|k|v) or 1; scale0 multiplies part 0 */
+int hd_mha_pack_heads(const void* src, void* dst, int N, int S, int C, int heads, int parts, float scale0, hd_stream_t stream);
+int hd_mha_unpack_heads(const void* src, void* dst, int N, int S, int C, int heads, int parts, float scale0, hd_stream_t stream);
 int hd_mha_fwd(int dtype, const void* qkv, void* out, float* lse, int N, int S, int C, int heads, hd_stream_t stream);
 int hd_mha_bwd(int dtype, const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
                int N, int S, int C, int heads, hd_stream_t stream);

@@ -27,10 +27,15 @@ def _close(a, b, rtol, atol):
     return float((a.double() - b.double()).norm()) <= rtol * float(b.double().norm()) + atol
 
 
-def _check_grads(net, ref, tol):
+def _check_grads(net, ref, tol, yard=None):
+    """Per-parameter gradient check against the fp32 reference.  `yard` (bf16 only): the gradients of the SAME reference module
+    under torch.autocast(bfloat16) -- stock PyTorch's own bf16 noise on this input.  Some DynamicUNet parameters (the 8x8 middle
+    blocks behind four attention layers) sit at 11-13 % in BOTH bf16 evaluations (tests/tools/debug_hybrid_bf16_noise.py), so a
+    parameter passes at 4 tol or at 1.5x the yardstick's own error, and the median over parameters must not exceed the
+    yardstick's median by more than 20 %."""
     pr = dict(ref.named_parameters())
     gscale = max(float(p.grad.norm()) for p in pr.values() if p.grad is not None)
-    worst, n = ("", 0.0), 0
+    worst, n, rels, yrels = ("", 0.0), 0, [], []
     for k, p in net.named_parameters():
         if pr[k].grad is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
@@ -38,10 +43,32 @@ def _check_grads(net, ref, tol):
         n += 1
         assert p.grad is not None, k
         r = _rel(p.grad, pr[k].grad)
-        if not _close(p.grad, pr[k].grad, 4 * tol, 2e-3 * tol * gscale + 2e-5) and r > worst[1]:
+        rtol = 4 * tol
+        if yard is not None:
+            yr = _rel(yard[k], pr[k].grad)
+            rels.append(r)
+            yrels.append(yr)
+            rtol = max(rtol, 1.5 * yr)
+        if not _close(p.grad, pr[k].grad, rtol, 2e-3 * tol * gscale + 2e-5) and r > worst[1]:
             worst = (k, r)
     assert worst[0] == "", worst
+    if yard is not None:
+        med, ymed = sorted(rels)[len(rels) // 2], sorted(yrels)[len(yrels) // 2]
+        assert med <= 1.2 * ymed + 1e-3, (med, ymed)
     return n
+
+
+def _autocast_grads(ref, fwd, gy):
+    """Gradients of the reference module under torch.autocast(bfloat16); leaves ref's .grad cleared."""
+    for p in ref.parameters():
+        p.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        e = fwd()
+    e.float().backward(gy)
+    g = {k: p.grad.detach().clone() for k, p in ref.named_parameters() if p.grad is not None}
+    for p in ref.parameters():
+        p.grad = None
+    return g
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
@@ -90,9 +117,10 @@ def test_dynamic_unet_vs_reference(dtype, tol, context_zero):
     assert _rel(e.detach(), er.detach()) < tol, _rel(e.detach(), er.detach())
     assert [p.requires_grad for p in net.parameters()] == [p.requires_grad for p in ref.parameters()]
     gy = torch.randn_like(er)
+    yard = _autocast_grads(ref, lambda: ref(x, t, lab, context_zero=context_zero), gy) if dtype == torch.bfloat16 else None
     e.backward(gy)
     er.backward(gy)
-    assert _check_grads(net, ref, tol) > 100
+    assert _check_grads(net, ref, tol, yard) > 100
 
 
 def test_hybrid_sampler_graph_replay_vs_reference():

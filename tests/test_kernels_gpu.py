@@ -257,10 +257,13 @@ def test_attention_forward_backward(dtype, tol, S, C):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-5), (torch.bfloat16, 1e-2)])
-@pytest.mark.parametrize("S,C,heads", [(64, 32, 8), (256, 64, 8), (1024, 128, 8), (200, 256, 8), (100, 512, 8), (77, 64, 4)])
+@pytest.mark.parametrize("S,C,heads", [(64, 32, 8), (256, 64, 8), (1024, 128, 8), (200, 256, 8), (100, 512, 8), (77, 64, 4),
+                                       (1024, 256, 8), (512, 512, 8), (128, 256, 4)])
 def test_multihead_attention_forward_backward(dtype, tol, S, C, heads):
     """hd_mha_*: the attention core of nn.MultiheadAttention(C, heads) with q = k = v (ModelCondition.py:189,203-208), against
-    softmax(q_h k_h^T / sqrt(hd)) v_h per head in fp32; sequence lengths that are not multiples of the kernel's tiles included."""
+    softmax(q_h k_h^T / sqrt(hd)) v_h per head in fp32; sequence lengths that are not multiples of the kernel's tiles included.
+    bf16 with S % 128 == 0 and head dim 8..64 takes the tensor-core route (heads zero-padded onto the tcgen05 kernels), the rest
+    the CUDA-core kernels."""
     dev = torch.device("cuda")
     ops, emu = _ops(), EmuOps()
     torch.manual_seed(S + C)
@@ -279,6 +282,44 @@ def test_multihead_attention_forward_backward(dtype, tol, S, C, heads):
     rd = torch.empty(N, S, 3 * C, device=dev)
     emu.mha_bwd(qkv.float(), ro, dout.float(), rl, None, rd, N, S, C, heads)
     assert _rel(dqkv.float(), rd) < tol, _rel(dqkv.float(), rd)
+
+
+@pytest.mark.parametrize("S,C,heads", [(1024, 256, 8), (256, 128, 8), (384, 512, 8)])
+def test_multihead_attention_tensor_core_route_matches_cuda_core_kernels(S, C, heads):
+    """The two bf16 routes of ops.mha_* (padded heads on tcgen05 vs hd_mha_* on CUDA cores) on the same inputs; pack / unpack
+    round trip is the identity on the live channels and writes zeros elsewhere."""
+    dev = torch.device("cuda")
+    ops = _ops()
+    assert ops.mha_tc and ops._mha_tc(torch.empty(1, dtype=torch.bfloat16, device=dev), S, C, heads)
+    torch.manual_seed(S * 3 + C)
+    N, bf = 3, torch.bfloat16
+    qkv = (torch.randn(N, S, 3 * C, device=dev) * 1.5).to(bf)
+    pad = torch.full((N * heads, S, 384), float("nan"), dtype=bf, device=dev)
+    back = torch.full_like(qkv, float("nan"))
+    assert ops.lib.hd_mha_pack_heads(qkv.data_ptr(), pad.data_ptr(), N, S, C, heads, 3, 1.0, None) == 0
+    assert ops.lib.hd_mha_unpack_heads(pad.data_ptr(), back.data_ptr(), N, S, C, heads, 3, 1.0, None) == 0
+    assert torch.equal(back, qkv)
+    hd = C // heads
+    pv = pad.view(N, heads, S, 3, 128)
+    assert torch.equal(pv[..., :hd], qkv.view(N, S, 3, heads, hd).permute(0, 3, 1, 2, 4)) and bool((pv[..., hd:] == 0).all())
+    dout = torch.randn(N, S, C, device=dev).to(bf)
+    res = []
+    for tc in (True, False):
+        ops.mha_tc = tc
+        try:
+            out = torch.empty(N, S, C, dtype=bf, device=dev)
+            lse = torch.empty(N, heads, S, device=dev)
+            dqkv = torch.full_like(qkv, float("nan"))
+            delta = torch.empty(N, heads, S, device=dev)
+            before = ops.tc_launches
+            ops.mha_fwd(qkv, out, lse, N, S, C, heads)
+            ops.mha_bwd(qkv, out, dout, lse, delta, dqkv, N, S, C, heads)
+            assert (ops.tc_launches - before == 3) == tc
+            res.append((out.float(), lse, dqkv.float()))
+        finally:
+            ops.mha_tc = True
+    assert _rel(res[0][0], res[1][0]) < 1e-2 and _rel(res[0][1], res[1][1]) < 1e-4 and _rel(res[0][2], res[1][2]) < 1.5e-2, \
+        [_rel(a, b) for a, b in zip(res[0], res[1])]
 
 
 @pytest.mark.parametrize("S,N,qscale", [(128, 2, 1.0), (256, 3, 1.0), (1024, 2, 1.0), (4096, 1, 1.0), (1024, 2, 6.0), (2048, 1, 12.0)])
