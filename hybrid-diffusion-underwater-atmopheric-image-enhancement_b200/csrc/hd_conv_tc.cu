@@ -13,6 +13,7 @@
 // + residual, bf16 store.
 #include "hd_tc_common.cuh"
 #include <mutex>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace {
@@ -78,9 +79,14 @@ struct ConvTcParams {
     int dbg;                         // timing experiments only (HDIFF_CONV_DBG): 1 = epilogue does no work, 2 = producers load nothing
     int nprod;                       // issuing threads in use (<= stages: a producer must never be two ring laps ahead,
                                      // the parity wait on `empty` cannot tell 0 completed phases from 2)
+    int pair;                        // CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs take two adjacent pixel tiles of the same
+                                     // output-channel tile; each loads its own A and HALF of the weight tile, the leader issues M = 256
+                                     // MMAs for both.  Halves the weight traffic L2 -> shared memory (the ring fill that bounds the N = 128
+                                     // layers) and shrinks a stage from 65 to 41 KB (deeper ring, room for the staged epilogue)
 };
 
-template <bool kStats, bool kRes>   // kStats: the epilogue also accumulates p.chan_sums; kRes: a residual tensor is added (its loads are
+template <bool kStats, bool kRes, bool kPair>   // kPair: CTA-pair mode (a separate instantiation: a kernel that CONTAINS cta_group::2
+                                    // instructions cannot be launched without a cluster — "cluster misconfiguration"); kStats: the epilogue also accumulates p.chan_sums; kRes: a residual tensor is added (its loads are
                                     // prefetched).  Separate instantiations: the extra registers must not slow the plain epilogue down
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -88,7 +94,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                const __grid_constant__ CUtensorMap mapRes, const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_bytes = p.NT * 128;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const int b_rows = kPair ? p.NT / 2 : p.NT;          // rows of a weight tile held by this CTA
+    const int b_bytes = b_rows * 128;
     const int stage_bytes = p.a_slot + (p.wres ? 0 : (p.txm ? 3 : 1) * b_bytes);
     const int stage_tx = p.a_tx + (p.wres ? 0 : (p.txm ? 3 : 1) * b_bytes);
     uint8_t* stage_buf = smem + (size_t)p.stages * stage_bytes;                  // [2][128 pixels][64 channels] bf16 when p.stage_out
@@ -117,20 +125,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // two issuers: a stage is released by BOTH (its owner's tcgen05.commit + a plain arrive of the other, who only watched
         // it fill), so neither can fall a ring lap behind — a parity wait cannot tell phase L from phase L + 2
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.mma2 ? 2 : 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], p.mma2 == 2 ? 2 : 1); mbar_init(&tempty[a], kEpiWarps); }
+        // pair: the leader's `tempty` collects the epilogue warps of BOTH CTAs
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], p.mma2 == 2 ? 2 : 1); mbar_init(&tempty[a], kPair ? 2 * kEpiWarps : kEpiWarps); }
         mbar_init(wfull, 1);
         mbar_init(&res_full[0], 1); mbar_init(&res_full[1], 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) { if (kPair) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();       // pair: the peer's barriers must be initialised before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    // pair: the loops below walk PAIR tiles q = (pair of adjacent pixel tiles, output-channel tile); this CTA's tile of q:
+    const int total_tiles = kPair ? (p.m_tiles / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
+    auto tile_of = [&](int q) { return kPair ? ((q / p.n_tiles) * 2 + (int)rank) * p.n_tiles + q % p.n_tiles : q; };
+    const uint32_t full_lead = kPair ? mapa_shared(smem_u32(full), 0) : 0u;       // the leader's barriers, shared::cluster addresses
+    const uint32_t tempty_lead = kPair ? mapa_shared(smem_u32(tempty), 0) : 0u;
     // tiles of this CTA: strided over the grid, or (p.contig) one contiguous range — then a CTA stays inside one image for
     // ~100 tiles, which the staged statistics need (one flush of fp64 atomics per image change)
     int t_begin = blockIdx.x, t_end = total_tiles, t_step = gridDim.x;
+    if (kPair) { t_begin = blockIdx.x >> 1; t_step = gridDim.x >> 1; }
     if (p.contig) {
         const int per = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
         t_begin = blockIdx.x * per; t_end = t_begin + per < total_tiles ? t_begin + per : total_tiles; t_step = 1;
@@ -147,11 +161,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int kb = 0; kb < p.kb_w; ++kb)
                         tma_load_2d(wres_buf + (size_t)(nt * p.kb_w + kb) * b_bytes, &mapB, wfull, kb * 64, nt * p.NT);
             }
-            for (int tile = t_begin; tile < t_end; tile += t_step) {
+            for (int q = t_begin; q < t_end; q += t_step) {
+                const int tile = tile_of(q);
                 const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
                 const int tx_i = m_tile % p.tiles_x; const int r = m_tile / p.tiles_x;
                 const int ty_i = r % p.tiles_y; const int n = r / p.tiles_y;
                 const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
+                if (kPair) {
+                    // Both CTAs' copies complete on the LEADER's full barrier: its producer announces the bytes of both, the peer only
+                    // issues its copies.  A stage is released in both CTAs at once by the leader's multicast commit.
+                    const int b_row0 = n_tile * p.NT + (int)rank * b_rows;
+                    if (p.txm) {
+                        const int tap_stride = p.P_in * p.nchunk_c;
+                        for (int ty = 0; ty < 3; ++ty)
+                            for (int py = 0; py < p.P_in; ++py)
+                                for (int cc = 0; cc < p.nchunk_c; ++cc) {
+                                    if (turn == prod) {
+                                        mbar_wait(&empty[stage], phase ^ 1);
+                                        if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * (uint32_t)stage_tx);
+                                        const uint32_t fb = full_lead + 8u * (uint32_t)stage;
+                                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                                        if (cc < p.nchunk0) tma_load_5d_pair(sa, &mapA0, fb, cc * 64, x0 - 1, py, y0 + ty - 1, n);
+                                        else tma_load_5d_pair(sa, &mapA1, fb, (cc - p.nchunk0) * 64, x0 - 1, py, y0 + ty - 1, n);
+                                        const int kb0 = (ty * 3 * p.P_in + py) * p.nchunk_c + cc;
+                                        for (int tx = 0; tx < 3; ++tx)
+                                            tma_load_2d_pair(sa + p.a_slot + tx * b_bytes, &mapB, fb, (kb0 + tx * tap_stride) * 64, b_row0);
+                                    }
+                                    if (++turn == p.nprod) turn = 0;
+                                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                                }
+                    } else {
+                        int kb = 0;
+                        for (int ty = 0; ty < p.k; ++ty)
+                            for (int tx = 0; tx < p.k; ++tx)
+                                for (int py = 0; py < p.P_in; ++py)
+                                    for (int cc = 0; cc < p.nchunk_c; ++cc, ++kb) {
+                                        if (turn == prod) {
+                                            mbar_wait(&empty[stage], phase ^ 1);
+                                            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * (uint32_t)stage_tx);
+                                            const uint32_t fb = full_lead + 8u * (uint32_t)stage;
+                                            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                                            if (cc < p.nchunk0) tma_load_5d_pair(sa, &mapA0, fb, cc * 64, x0 + tx - p.pad, py, y0 + ty - p.pad, n);
+                                            else tma_load_5d_pair(sa, &mapA1, fb, (cc - p.nchunk0) * 64, x0 + tx - p.pad, py, y0 + ty - p.pad, n);
+                                            tma_load_2d_pair(sa + p.a_slot, &mapB, fb, kb * 64, b_row0);
+                                        }
+                                        if (++turn == p.nprod) turn = 0;
+                                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                                    }
+                    }
+                    continue;
+                }
                 // K order = (tap row, tap column, parity row, 64-channel chunk); plain counters, no divisions: this
                 // single thread's loop rate bounds how fast shared memory can be filled
                 if (p.txm) {
@@ -203,7 +262,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
     } else if (warp == 1 || warp == kSecondMma) {
         const int me = warp == 1 ? 0 : 1;            // this issuer's tile parity = its accumulator
-        if ((me == 0 || p.mma2) && elect_one()) {
+        if (kPair) {
+            // the leader's first issuer drives both SMs: M = 256 (this CTA's 128 pixels + the peer's), B halves from both CTAs
+            if (me == 0 && rank == 0 && elect_one()) {
+                const uint32_t idesc = umma_idesc_bf16(256, p.NT, 0, 0);
+                int stage = 0; uint32_t phase = 0; int it = 0;
+                const uint32_t ring_lo = umma_desc_lo(smem_u32(smem));
+                const uint32_t st16 = (uint32_t)stage_bytes >> 4, aslot16 = (uint32_t)p.a_slot >> 4, b16 = (uint32_t)b_bytes >> 4;
+                uint32_t a_lo = ring_lo;
+                for (int q = t_begin; q < t_end; q += t_step, ++it) {
+                    const int acc = it & 1;
+                    mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * 256;
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t b_lo = a_lo + aslot16;
+                        if (p.txm) {
+#pragma unroll
+                            for (int tx = 0; tx < 3; ++tx)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16_lo_pair(d_tmem, a_lo + tx * 8 + 2 * k, b_lo + tx * b16 + 2 * k, idesc, (kb | tx | k) != 0);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_lo_pair(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        umma_commit_pair(&empty[stage], 3);
+                        a_lo += st16;
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; a_lo = ring_lo; }
+                    }
+                    umma_commit_pair(&tfull[acc], 3);
+                }
+            }
+        } else if ((me == 0 || p.mma2) && elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, p.NT, 0, 0);
             int stage = 0; uint32_t phase = 0; int it = 0;
             if (p.wres) { mbar_wait(wfull, 0); tc_fence_after(); }
@@ -214,7 +308,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint32_t wres_lo = umma_desc_lo(smem_u32(wres_buf));
             const uint32_t bstep = p.wres ? (uint32_t)per_row * b16 : b16;         // between the B tiles of two tap columns (txm)
             uint32_t a_lo = ring_lo;                     // A operand of the current stage
-            for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
+            for (int q = t_begin; q < t_end; q += t_step, ++it) {
+                const int tile = tile_of(q);
                 const int acc = it & 1;
                 if (p.mma2 == 2) {
                     // both issuers, every stage: K slices k = me, me + 2 of each operand pair into partial accumulator `me`
@@ -308,7 +403,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // at the next tile's barrier; 64->64 + residual 291 us against 199 us without one)
         constexpr int kResIssuer = 32;
         const bool early_res = kRes && p.stage_out && p.NT == 64;
-        if (kRes && p.stage_out && etid == kResIssuer && t_begin < t_end) res_load(t_begin, 0, 0);
+        if (kRes && p.stage_out && etid == kResIssuer && t_begin < t_end) res_load(tile_of(t_begin), 0, 0);
+        // hand an accumulator back to the MMA issuer (pair: the leader's barrier collects both CTAs' warps)
+        auto release_acc = [&](int acc) {
+            if (kPair) mbar_arrive_cluster(tempty_lead + 8u * (uint32_t)acc); else mbar_arrive(&tempty[acc]);
+        };
         // staged epilogue + statistics (Cout == 64: one block per tile): per-channel (sum, sum of squares) of the STORED bf16
         // values are read back out of the staged tile; every warp keeps the sums of its 16 pixel rows in registers (lane:
         // channels 2 lane, 2 lane + 1) across this CTA's consecutive tiles of one image and adds them to p.chan_sums (fp64
@@ -321,7 +420,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             atomicAdd(d, (double)st_s0); atomicAdd(d + 1, (double)st_q0); atomicAdd(d + 2, (double)st_s1); atomicAdd(d + 3, (double)st_q1);
             st_s0 = st_q0 = st_s1 = st_q1 = 0.f;
         };
-        for (int tile = t_begin; tile < t_end; tile += t_step, ++it) {
+        for (int q = t_begin; q < t_end; q += t_step, ++it) {
+            const int tile = tile_of(q);
             const int acc = it & 1;
             const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
             const int tx_i = m_tile % p.tiles_x; const int r = m_tile / p.tiles_x;
@@ -345,9 +445,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 return a;
             };
             if (it == 0 && etid < p.NT) add_t[etid] = addend_load(tile);
-            const bool has_next = tile + t_step < t_end;
+            const bool has_next = q + t_step < t_end;
+            const int tile_next = has_next ? tile_of(q + t_step) : tile;
             float a_next = 0.f;
-            if (has_next) a_next = addend_load(tile + t_step);
+            if (has_next) a_next = addend_load(tile_next);
             if (kStats) for (int c = etid; c < 2 * p.NT; c += 32 * kEpiWarps) stat_s[acc * 512 + c] = 0.f;
             asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps only: this tile's addend is staged
             if (sstat && n != n_prev) {
@@ -384,14 +485,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 // Requesting tile i+1's residual NOW (not after this tile's store) puts it a full epilogue earlier into the TMA
                 // queue, which the four producer threads keep ~3 operand stages deep.
                 bulk_wait_group_read0();
-                res_load(tile + t_step, 0, (sb + 1) & 1);
+                res_load(tile_next, 0, (sb + 1) & 1);
             }
             mbar_wait(&tfull[acc], (it >> 1) & 1);
             tc_fence_after();
             if (HD_CONV_DBG(p) & 1) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) release_acc(acc);
                 if (has_next && etid < p.NT) addend[(acc ^ 1) * 256 + etid] = a_next;
                 continue;
             }
@@ -463,7 +564,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     if (c + 64 >= p.NT) {               // last TMEM read of the tile: hand the accumulator back to the MMA issuers now,
                         tc_fence_before();              // not after the staging, the barrier and the statistics below
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                        if (lane == 0) release_acc(acc);
                     }
                     uint8_t* sbuf = stage_buf + (sb & 1) * kABytes;
                     if (kRes) mbar_wait(&res_full[sb & 1], (sb >> 1) & 1);
@@ -484,7 +585,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     if (kRes && etid == kResIssuer) {      // the other buffer is free (thread 0 saw its store read out before it joined the
                                                            // barrier above): fetch the next residual block
                         if (c + 64 < p.NT) res_load(tile, (c - half * 16) / 64 + 1, (sb + 1) & 1);
-                        else if (has_next && !early_res) res_load(tile + t_step, 0, (sb + 1) & 1);
+                        else if (has_next && !early_res) res_load(tile_next, 0, (sb + 1) & 1);
                     }
                     if (sstat) {         // this warp: 16 of the 128 staged pixel rows; lane: channels 2 lane, 2 lane + 1 of the block
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f, s2 = 0.f, s3 = 0.f, q2 = 0.f, q3 = 0.f;
@@ -596,7 +697,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (!p.stage_out) {                      // (the staged epilogue released the accumulator after its last TMEM load)
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) release_acc(acc);
             }
             if (has_next && etid < p.NT) addend[(acc ^ 1) * 256 + etid] = a_next;     // visible after the next iteration's barrier
             if (kStats) {
@@ -609,8 +710,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (p.stage_out && etid == 0) bulk_wait_group0();           // shared memory must outlive the last tensor store
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (kPair) cluster_sync_all(); else __syncthreads();       // pair: the leader's MMAs read the peer's shared memory until the last tile
+    if (warp == 1) { tc_fence_after(); if (kPair) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 #ifdef HDIFF_LAB
     if ((p.dbg & 4) && blockIdx.x == 0 && threadIdx.x == 0) {
         long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -636,6 +737,8 @@ bool conv_geometry(int H, int W, int* TH, int* TW) {
 }
 
 
+static bool pair_env_on() { static const bool on = !getenv("HDIFF_CONV_PAIR") || atoi(getenv("HDIFF_CONV_PAIR")) > 0; return on; }
+
 // Shared-memory plan and kernel modes of a launch (p.N .. p.kblocks, p.NT, p.kb_w already set).  Returns false when nothing fits.
 static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out, int ksize, int out_nchw_c, bool chan_sums,
                       bool allow_stage, bool has_res = false) {
@@ -648,15 +751,26 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
         static const bool wres_on = getenv("HDIFF_CONV_WRES") != nullptr;    // measured: no gain (the operand fetch of the MMAs bounds
                                                                              // the kernel, not the TMA fill), so off by default
         static const int stage_env = getenv("HDIFF_CONV_STAGE") ? atoi(getenv("HDIFF_CONV_STAGE")) : 2;   // 0 off, 1 1x1 only, 2 every eligible conv
-        const int budget = 200 * 1024;
+        static const int budget_kb = getenv("HDIFF_CONV_BUDGET") ? atoi(getenv("HDIFF_CONV_BUDGET")) : 200;
+        const int budget = budget_kb * 1024;
         const long long wbytes = (long long)CoutL * p.kb_w * 128;
         const bool want_txm = !txm_off && ksize == 3 && p.TH == 1 && p.TW == 128;
-        const bool want_wres = wres_on && wbytes <= 96 * 1024;
+        const bool want_wres = wres_on && wbytes <= 96 * 1024 && !(pair_env_on() && ksize == 3 && (p.NT == 128 || p.NT == 256));
         const bool want_stage = allow_stage && out_nchw_c == 0 && p.NT % 64 == 0 && Cout % 64 == 0 &&
                                 (stage_env == 2 || (stage_env == 1 && ksize == 1));
         const int txm_a_tx = (p.TW + 2) * 128, txm_a_slot = (txm_a_tx + 1023) / 1024 * 1024;
+        // CTA pair (see ConvTcParams::pair), 3x3 layers with an even number of pixel tiles.  By shape, from scripts/conv_pair_bench.py
+        // (profiles/r02_conv_pair.txt): 128-channel tiles in shifted-operand mode -13..-22 % (the 41 KB stage also leaves room for the
+        // staged epilogue, which is half of the gain), 256-channel tiles -1..-15 %, 64-channel tiles only when a tile has many K blocks
+        // (128+64 -> 64: -10 %; 64 -> 64 gets slower: its epilogue, not its ring, is the limit).  HDIFF_CONV_PAIR=0 switches the mode
+        // off, =3 forces it for every 3x3 layer with 64 / 128 / 256-channel tiles.
+        static const int pair_env = getenv("HDIFF_CONV_PAIR") ? atoi(getenv("HDIFF_CONV_PAIR")) : 1;
+        const bool pair_shape = pair_env >= 3 ? (p.NT == 64 || p.NT == 128 || p.NT == 256)
+                                              : ((p.NT == 128 && want_txm) || p.NT == 256 || (p.NT == 64 && want_txm && p.nchunk_c * P_in >= 3));
+        const bool pair = pair_env > 0 && ksize == 3 && pair_shape && !chan_sums && out_nchw_c == 0 && p.m_tiles % 2 == 0 && p.m_tiles >= 2;
+        const int b_rows = pair ? p.NT / 2 : p.NT;
         auto stages_of = [&](bool txm, bool wres, bool stage) {
-            const int sbytes = (txm ? txm_a_slot : kABytes) + (wres ? 0 : (txm ? 3 : 1) * p.NT * 128);
+            const int sbytes = (txm ? txm_a_slot : kABytes) + (wres ? 0 : (txm ? 3 : 1) * b_rows * 128);
             const long long avail = budget - (stage ? 2 * kABytes : 0) - (wres ? wbytes : 0);
             return avail <= 0 ? 0 : (int)(avail / sbytes);
         };
@@ -667,6 +781,13 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
                     if (stages_of(t, w, g) >= (t ? 3 : 2)) { txm = t; wres = w; stage = g; found = true; }
         if (!found) return false;
         p.txm = txm; p.wres = wres; p.stage_out = stage;
+        p.pair = pair && !wres;
+        if (pair && !p.pair) {                      // planned with half weight tiles but the pair was dropped: plan again without it
+            ConvTcParams q = p; q.m_tiles = 1;      // (an odd tile count switches the pair off)
+            if (!conv_plan(q, CoutL, Cout, P_in, P_out, ksize, out_nchw_c, chan_sums, allow_stage, has_res)) return false;
+            q.m_tiles = p.m_tiles; p = q;
+            return true;
+        }
 #ifdef HDIFF_LAB
         static const int dbg = getenv("HDIFF_CONV_DBG") ? atoi(getenv("HDIFF_CONV_DBG")) : 0;
         p.dbg = dbg;
@@ -688,6 +809,7 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
         else if (p.NT <= 128 && ksize == 3) mode = (p.txm && P_in == 1) ? 0 : 2;
         p.mma2 = mma2_env >= 0 ? mma2_env : mode;
         if (p.mma2 == 2 && (p.NT > 128 || p.wres)) p.mma2 = p.NT <= 64 ? 1 : 0;
+        if (p.pair) p.mma2 = 0;                         // one issuer (the leader's) for both SMs
         p.a_slot = txm ? txm_a_slot : kABytes; p.a_tx = txm ? txm_a_tx : kABytes;
         if (txm) p.kblocks = 3 * P_in * p.nchunk_c;       // stages per tile: one per (tap row, parity row, chunk)
         p.stages = stages_of(txm, wres, stage); if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -772,7 +894,7 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     // statistics in the staged epilogue handle one 64-channel block per tile; other widths with `chan_sums` take the direct-store
     // epilogue and its register butterfly
     HD_REQUIRE(conv_plan(p, CoutL, Cout, P_in, P_out, ksize, out_nchw_c, chan_sums != nullptr, !chan_sums || Cout == 64, res != nullptr));
-    const int stage_bytes = p.a_slot + (p.wres ? 0 : (p.txm ? 3 : 1) * p.NT * 128);
+    const int stage_bytes = p.a_slot + (p.wres ? 0 : (p.txm ? 3 : 1) * (p.pair ? p.NT / 2 : p.NT) * 128);
     p.nprod = p.stages < kProducers ? p.stages : kProducers;
     p.Cout = Cout; p.P_out = P_out;
     p.bias = bias; p.emb = emb; p.emb_stride = emb_stride;
@@ -794,27 +916,46 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     {
         uint64_t dims[2] = {(uint64_t)ksize * ksize * CinL, (uint64_t)CoutL};
         uint64_t str[1] = {(uint64_t)ksize * ksize * CinL};
-        uint32_t box[2] = {64, (uint32_t)p.NT};
+        uint32_t box[2] = {64, (uint32_t)(p.pair ? p.NT / 2 : p.NT)};
         rc = hd_make_tmap_bf16(&mB, w, 2, dims, str, box); if (rc) return rc;
     }
     const size_t smem = (size_t)p.stages * stage_bytes + (p.stage_out ? 2 * kABytes : 0) + (p.wres ? (size_t)CoutL * p.kb_w * 128 : 0) + 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 2 * 256 * 4 + 2 * 512 * 4;
     static unsigned long long attr_set = 0;
     if (!hd_seen_on_device(&attr_set)) {
-        if (cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        if (cudaFuncSetAttribute(conv_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
             hd_set_error("cudaFuncSetAttribute(conv_tc_kernel)"); return HD_ERR_CUDA;
         }
         hd_mark_on_device(&attr_set);
     }
     int grid = p.m_tiles * p.n_tiles; const int sms = hd_num_sms(); if (grid > sms) grid = sms;
+    static const bool verbose = getenv("HDIFF_CONV_VERBOSE") != nullptr;
+    if (verbose)
+        fprintf(stderr, "hd_conv_tc: N%d %dx%d %d+%d(P%d)->%d(P%d) k%d NT%d | pair %d txm %d stage_out %d wres %d mma2 %d stages %d stage_bytes %d smem %zu grid %d\n",
+                N, H, W, C0, C1, P_in, Cout, P_out, ksize, p.NT, p.pair, p.txm, p.stage_out, p.wres, p.mma2, p.stages, stage_bytes, smem, grid);
+    if (p.pair) {
+        grid &= ~1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        const cudaError_t e = res ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, true>, mA0, mA1, mB, mOut, mRes, p)
+                                  : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, true>, mA0, mA1, mB, mOut, mRes, p);
+        if (e != cudaSuccess) { hd_set_error(cudaGetErrorString(e)); return HD_ERR_CUDA; }
+        HD_CHECK_LAUNCH();
+        return HD_OK;
+    }
     if (chan_sums && !p.stage_out) {          // (the staged epilogue takes its statistics from the staged tile, no template flag)
-        if (res) conv_tc_kernel<true, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
-        else conv_tc_kernel<true, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
+        if (res) conv_tc_kernel<true, true, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
+        else conv_tc_kernel<true, false, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
     } else {
-        if (res) conv_tc_kernel<false, true><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
-        else conv_tc_kernel<false, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
+        if (res) conv_tc_kernel<false, true, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
+        else conv_tc_kernel<false, false, false><<<grid, kThreads, smem, stream>>>(mA0, mA1, mB, mOut, mRes, p);
     }
     HD_CHECK_LAUNCH();
     return HD_OK;
