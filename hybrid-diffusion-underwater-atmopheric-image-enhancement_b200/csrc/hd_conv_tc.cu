@@ -761,12 +761,12 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
         const int txm_a_tx = (p.TW + 2) * 128, txm_a_slot = (txm_a_tx + 1023) / 1024 * 1024;
         // CTA pair (see ConvTcParams::pair), 3x3 layers with an even number of pixel tiles.  By shape, from scripts/conv_pair_bench.py
         // (profiles/r02_conv_pair.txt): 128-channel tiles in shifted-operand mode -13..-22 % (the 41 KB stage also leaves room for the
-        // staged epilogue, which is half of the gain), 256-channel tiles -1..-15 %, 64-channel tiles only when a tile has many K blocks
-        // (128+64 -> 64: -10 %; 64 -> 64 gets slower: its epilogue, not its ring, is the limit).  HDIFF_CONV_PAIR=0 switches the mode
+        // staged epilogue, which is half of the gain), 256-channel tiles -1..-15 %, 64-channel tiles only with >= 2 K chunks per tap
+        // (128+64 -> 64: -10 %, 128 -> 64: -2..-10 %; 64 -> 64 gets slower: its epilogue, not its ring, is the limit).  HDIFF_CONV_PAIR=0 switches the mode
         // off, =3 forces it for every 3x3 layer with 64 / 128 / 256-channel tiles.
         static const int pair_env = getenv("HDIFF_CONV_PAIR") ? atoi(getenv("HDIFF_CONV_PAIR")) : 1;
         const bool pair_shape = pair_env >= 3 ? (p.NT == 64 || p.NT == 128 || p.NT == 256)
-                                              : ((p.NT == 128 && want_txm) || p.NT == 256 || (p.NT == 64 && want_txm && p.nchunk_c * P_in >= 3));
+                                              : ((p.NT == 128 && want_txm) || p.NT == 256 || (p.NT == 64 && want_txm && p.nchunk_c * P_in >= 2));
         const bool pair = pair_env > 0 && ksize == 3 && pair_shape && !chan_sums && out_nchw_c == 0 && p.m_tiles % 2 == 0 && p.m_tiles >= 2;
         const int b_rows = pair ? p.NT / 2 : p.NT;
         auto stages_of = [&](bool txm, bool wres, bool stage) {

@@ -15,7 +15,8 @@ sys.path.insert(0, ROOT)
 CASES = ((32, 128, 128, 128, 0, 128, 0), (32, 128, 128, 128, 0, 128, 1), (32, 256, 256, 128, 0, 128, 0), (32, 256, 256, 64, 0, 128, 0),
          (32, 128, 128, 256, 0, 128, 1), (32, 128, 128, 128, 0, 256, 0), (16, 128, 128, 256, 0, 256, 1), (16, 256, 256, 128, 0, 128, 1),
          (16, 128, 128, 256, 128, 256, 0), (32, 64, 64, 128, 0, 128, 0), (16, 64, 64, 256, 0, 256, 1), (3, 128, 128, 128, 0, 128, 1),
-         (32, 256, 256, 64, 0, 64, 0), (32, 256, 256, 64, 0, 64, 1), (32, 256, 256, 128, 64, 64, 1), (32, 128, 128, 64, 0, 64, 0))
+         (32, 256, 256, 64, 0, 64, 0), (32, 256, 256, 64, 0, 64, 1), (32, 256, 256, 128, 64, 64, 1), (32, 128, 128, 64, 0, 64, 0),
+         (32, 256, 256, 128, 0, 64, 1), (32, 256, 256, 192, 0, 64, 1), (32, 128, 128, 128, 0, 64, 0))
 
 
 def one():
