@@ -57,6 +57,25 @@ __device__ __forceinline__ void add_res_bf16x8(uint4& o, const uint4& r) {
     for (int i = 0; i < 4; ++i) a[i] = __hadd2(a[i], b[i]);
 }
 
+// Division by a launch constant without the ~25-instruction integer-division sequence: q = umulhi(x, mul) >> shr for 0 <= x < 2^31
+// (mul = ceil(2^(31 + ceil_log2 d) / d)).  ncu source view of a 64->64 launch: the three div/mod pairs of the tile decomposition were
+// 82 of ~400 instructions of an epilogue warp per tile, and that warp's in-order instruction chain IS the tile period of the K = 576 layers.
+struct FastDiv {
+    uint32_t mul, shr, d;
+    __device__ __forceinline__ int div(int x) const { return d == 1 ? x : (int)(__umulhi((uint32_t)x, mul) >> shr); }
+    __device__ __forceinline__ void divmod(int x, int& q, int& r) const { q = div(x); r = x - q * (int)d; }
+};
+static FastDiv make_fastdiv(int d) {
+    FastDiv f{0u, 0u, (uint32_t)d};
+    if (d > 1) {
+        int lg = 0; while ((1ll << lg) < d) ++lg;
+        const int pw = 31 + lg;
+        f.mul = (uint32_t)(((1ull << pw) + (uint64_t)d - 1) / (uint64_t)d);
+        f.shr = (uint32_t)(pw - 32);
+    }
+    return f;
+}
+
 struct ConvTcParams {
     int N, H, W, TH, TW, tiles_x, tiles_y, m_tiles, n_tiles, NT;
     int k, pad, P_in, nchunk0, nchunk_c, kblocks, stages;
@@ -79,6 +98,7 @@ struct ConvTcParams {
     int dbg;                         // timing experiments only (HDIFF_CONV_DBG): 1 = epilogue does no work, 2 = producers load nothing
     int nprod;                       // issuing threads in use (<= stages: a producer must never be two ring laps ahead,
                                      // the parity wait on `empty` cannot tell 0 completed phases from 2)
+    FastDiv fd_nt, fd_tx, fd_ty, fd_txy;   // n_tiles, tiles_x, tiles_y, tiles_x * tiles_y
     int pair;                        // CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs take two adjacent pixel tiles of the same
                                      // output-channel tile; each loads its own A and HALF of the weight tile, the leader issues M = 256
                                      // MMAs for both.  Halves the weight traffic L2 -> shared memory (the ring fill that bounds the N = 128
@@ -138,7 +158,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
     // pair: the loops below walk PAIR tiles q = (pair of adjacent pixel tiles, output-channel tile); this CTA's tile of q:
     const int total_tiles = kPair ? (p.m_tiles / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
-    auto tile_of = [&](int q) { return kPair ? ((q / p.n_tiles) * 2 + (int)rank) * p.n_tiles + q % p.n_tiles : q; };
+    auto tile_of = [&](int q) {
+        if (!kPair) return q;
+        int mp, nt; p.fd_nt.divmod(q, mp, nt);
+        return (mp * 2 + (int)rank) * p.n_tiles + nt;
+    };
+    // tile -> (output-channel tile, x tile, y tile, image)
+    auto decompose = [&](int tile, int& n_tile, int& tx_i, int& ty_i, int& n) {
+        int m_tile, r;
+        p.fd_nt.divmod(tile, m_tile, n_tile);
+        p.fd_tx.divmod(m_tile, r, tx_i);
+        p.fd_ty.divmod(r, n, ty_i);
+    };
     const uint32_t full_lead = kPair ? mapa_shared(smem_u32(full), 0) : 0u;       // the leader's barriers, shared::cluster addresses
     const uint32_t tempty_lead = kPair ? mapa_shared(smem_u32(tempty), 0) : 0u;
     // tiles of this CTA: strided over the grid, or (p.contig) one contiguous range — then a CTA stays inside one image for
@@ -163,9 +194,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             for (int q = t_begin; q < t_end; q += t_step) {
                 const int tile = tile_of(q);
-                const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
-                const int tx_i = m_tile % p.tiles_x; const int r = m_tile / p.tiles_x;
-                const int ty_i = r % p.tiles_y; const int n = r / p.tiles_y;
+                int n_tile, tx_i, ty_i, n;
+                decompose(tile, n_tile, tx_i, ty_i, n);
                 const int x0 = tx_i * p.TW, y0 = ty_i * p.TH;
                 if (kPair) {
                     // Both CTAs' copies complete on the LEADER's full barrier: its producer announces the bytes of both, the peer only
@@ -350,7 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
-                const uint32_t wb_lo = wres_lo + (uint32_t)((tile % p.n_tiles) * p.kb_w) * b16;
+                const uint32_t wb_lo = wres_lo + (uint32_t)((tile - p.fd_nt.div(tile) * p.n_tiles) * p.kb_w) * b16;
                 uint32_t wk_lo = wb_lo;                  // resident weights: B tile of this stage's first K block
                 int in_row = 0;
                 for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -389,9 +419,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // staged epilogue + residual: the residual block is brought into the staging buffer by TMA one block ahead (issued
         // by thread 0 right after the barrier that frees the buffer) and the output is formed in place over it
         auto res_load = [&](int tl, int blk, uint32_t buf) {
-            const int nt = tl % p.n_tiles, mt = tl / p.n_tiles;
-            const int txi = mt % p.tiles_x; const int rr = mt / p.tiles_x;
-            const int tyi = rr % p.tiles_y; const int nn = rr / p.tiles_y;
+            int nt, txi, tyi, nn;
+            decompose(tl, nt, txi, tyi, nn);
             const int j0 = nt * p.NT + blk * 64;
             const int cv_w = p.P_out * p.Cout;
             const int py = j0 / cv_w;
@@ -423,9 +452,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         for (int q = t_begin; q < t_end; q += t_step, ++it) {
             const int tile = tile_of(q);
             const int acc = it & 1;
-            const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
-            const int tx_i = m_tile % p.tiles_x; const int r = m_tile / p.tiles_x;
-            const int ty_i = r % p.tiles_y; const int n = r / p.tiles_y;
+            int n_tile, tx_i, ty_i, n;
+            decompose(tile, n_tile, tx_i, ty_i, n);
             const int y = ty_i * p.TH + ty, x = tx_i * p.TW + tx;
             const bool valid = y < p.H;
             // per-channel addend (bias + this image's embedding row) staged once per tile while the MMAs still run; the
@@ -437,7 +465,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             auto addend_load = [&](int tl) {
                 float a = 0.f;
                 if (etid < p.NT) {
-                    const int nt = tl % p.n_tiles, nn = (tl / p.n_tiles) / (p.tiles_x * p.tiles_y);
+                    int mt, nt; p.fd_nt.divmod(tl, mt, nt);
+                    const int nn = p.fd_txy.div(mt);
                     const int j = nt * p.NT + etid;
                     if (p.bias) a = __ldg(p.bias + j);
                     if (p.emb) a += __ldg(p.emb + (long long)nn * p.emb_stride + j);
@@ -457,8 +486,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             // element offset of this thread's pixel for output-channel 0 of each parity (P_out == 2 stores the four
             // parities of the transposed convolution through the 2x2 view); hoisted out of the chunk loop
-            const long long pix1 = (((long long)n * p.H + y) * p.W + x) * p.Cout;
-            const long long pix2 = (((long long)n * (2 * p.H) + 2 * y) * (2 * p.W) + 2 * x) * p.Cout;
+            long long pix1 = 0, pix2 = 0;
+            if (!p.stage_out) {          // only the direct-store epilogue addresses global memory itself
+                pix1 = (((long long)n * p.H + y) * p.W + x) * p.Cout;
+                pix2 = (((long long)n * (2 * p.H) + 2 * y) * (2 * p.W) + 2 * x) * p.Cout;
+            }
             const long long q_dx = p.Cout, q_dy = 2ll * p.W * p.Cout;
             uint4 pre_a[2], pre_b[2];
             const bool have_pre = kRes && valid && !p.out_nchw && !p.stage_out && half * 16 < p.NT;
@@ -885,6 +917,8 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
     p.m_tiles = N * p.tiles_x * p.tiles_y;
     const int CoutL = Cout * P_out * P_out;
     p.NT = pick_nt(CoutL); p.n_tiles = CoutL / p.NT;
+    p.fd_nt = make_fastdiv(p.n_tiles); p.fd_tx = make_fastdiv(p.tiles_x); p.fd_ty = make_fastdiv(p.tiles_y);
+    p.fd_txy = make_fastdiv(p.tiles_x * p.tiles_y);
     p.k = ksize; p.pad = ksize / 2; p.P_in = P_in;
     if (P_in == 1) { p.nchunk0 = C0 / 64; p.nchunk_c = (C0 + C1) / 64; }
     else { p.nchunk0 = 2 * C0 / 64; p.nchunk_c = p.nchunk0; }
