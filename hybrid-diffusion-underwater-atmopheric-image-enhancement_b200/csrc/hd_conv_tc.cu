@@ -838,6 +838,9 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
         // K = 576 tiles WITH a residual are bound by their epilogue (lab build: MMA stream alone 0.142 ms, + epilogue 0.196, + residual
         // 0.262 at 64->64 @256^2); there the partial accumulators of mode 2 only add epilogue work: one issuer 0.247 ms
         if (p.NT <= 64 && ksize == 3 && has_res && p.nchunk_c * P_in <= 1) mode = 0;
+        // ... and WITHOUT a residual by alternate tiles (mode 1: two accumulators, no partial sums for the epilogue to add): 64->64
+        // @256^2 0.200 -> 0.171 ms, @128^2 0.063 -> 0.050 ms (profiles/r02_conv_pair.txt)
+        else if (p.NT <= 64 && ksize == 3 && p.nchunk_c * P_in <= 1) mode = 1;
         else if (p.NT <= 128 && ksize == 3) mode = (p.txm && P_in == 1) ? 0 : 2;
         p.mma2 = mma2_env >= 0 ? mma2_env : mode;
         if (p.mma2 == 2 && (p.NT > 128 || p.wres)) p.mma2 = p.NT <= 64 ? 1 : 0;
