@@ -177,8 +177,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     int t_begin = blockIdx.x, t_end = total_tiles, t_step = gridDim.x;
     if (kPair) { t_begin = blockIdx.x >> 1; t_step = gridDim.x >> 1; }
     if (p.contig) {
-        const int per = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-        t_begin = blockIdx.x * per; t_end = t_begin + per < total_tiles ? t_begin + per : total_tiles; t_step = 1;
+        const int walkers = kPair ? (int)gridDim.x >> 1 : (int)gridDim.x, me = kPair ? (int)blockIdx.x >> 1 : (int)blockIdx.x;
+        const int per = (total_tiles + walkers - 1) / walkers;
+        t_begin = me * per; t_end = t_begin + per < total_tiles ? t_begin + per : total_tiles; t_step = 1;
     }
 
     if (warp == 0 || warp >= kFirstExtraProducer) {
@@ -769,6 +770,9 @@ bool conv_geometry(int H, int W, int* TH, int* TW) {
 }
 
 
+// set when a cluster launch was refused on this system (e.g. a partition without co-schedulable SM pairs): the one-CTA kernel
+// takes over for the rest of the process
+static int g_pair_refused = 0;
 static bool pair_env_on() { static const bool on = !getenv("HDIFF_CONV_PAIR") || atoi(getenv("HDIFF_CONV_PAIR")) > 0; return on; }
 
 // Shared-memory plan and kernel modes of a launch (p.N .. p.kblocks, p.NT, p.kb_w already set).  Returns false when nothing fits.
@@ -791,15 +795,13 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
         const bool want_stage = allow_stage && out_nchw_c == 0 && p.NT % 64 == 0 && Cout % 64 == 0 &&
                                 (stage_env == 2 || (stage_env == 1 && ksize == 1));
         const int txm_a_tx = (p.TW + 2) * 128, txm_a_slot = (txm_a_tx + 1023) / 1024 * 1024;
-        // CTA pair (see ConvTcParams::pair), 3x3 layers with an even number of pixel tiles.  By shape, from scripts/conv_pair_bench.py
-        // (profiles/r02_conv_pair.txt): 128-channel tiles in shifted-operand mode -13..-22 % (the 41 KB stage also leaves room for the
-        // staged epilogue, which is half of the gain), 256-channel tiles -1..-15 %, 64-channel tiles only with >= 2 K chunks per tap
-        // (128+64 -> 64: -10 %, 128 -> 64: -2..-10 %; 64 -> 64 gets slower: its epilogue, not its ring, is the limit).  HDIFF_CONV_PAIR=0 switches the mode
-        // off, =3 forces it for every 3x3 layer with 64 / 128 / 256-channel tiles.
+        // CTA pair (see ConvTcParams::pair): every 3x3 layer with 64-, 128- or 256-channel tiles and an even number of pixel tiles.
+        // scripts/conv_pair_bench.py (profiles/r02_conv_pair.txt): 128-channel tiles -25 % (128->128 @128^2 0.142 -> 0.107 ms; the 41 KB
+        // stage also leaves room for the staged epilogue), 64->128 @256^2 -35 %, 256-channel tiles -10..-15 %, 64-channel tiles -4..-20 %.
+        // HDIFF_CONV_PAIR=0 switches the mode off.
         static const int pair_env = getenv("HDIFF_CONV_PAIR") ? atoi(getenv("HDIFF_CONV_PAIR")) : 1;
-        const bool pair_shape = pair_env >= 3 ? (p.NT == 64 || p.NT == 128 || p.NT == 256)
-                                              : ((p.NT == 128 && want_txm) || p.NT == 256 || (p.NT == 64 && want_txm && p.nchunk_c * P_in >= 2));
-        const bool pair = pair_env > 0 && ksize == 3 && pair_shape && !chan_sums && out_nchw_c == 0 && p.m_tiles % 2 == 0 && p.m_tiles >= 2;
+        const bool pair_shape = p.NT == 64 || p.NT == 128 || p.NT == 256;
+        const bool pair = pair_env > 0 && !g_pair_refused && ksize == 3 && pair_shape && out_nchw_c == 0 && p.m_tiles % 2 == 0 && p.m_tiles >= 2;
         const int b_rows = pair ? p.NT / 2 : p.NT;
         auto stages_of = [&](bool txm, bool wres, bool stage) {
             const int sbytes = (txm ? txm_a_slot : kABytes) + (wres ? 0 : (txm ? 3 : 1) * b_rows * 128);
@@ -813,7 +815,7 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
                     if (stages_of(t, w, g) >= (t ? 3 : 2)) { txm = t; wres = w; stage = g; found = true; }
         if (!found) return false;
         p.txm = txm; p.wres = wres; p.stage_out = stage;
-        p.pair = pair && !wres;
+        p.pair = pair && !wres && (!chan_sums || stage);      // statistics: only the staged epilogue's (no template flag) in pair mode
         if (pair && !p.pair) {                      // planned with half weight tiles but the pair was dropped: plan again without it
             ConvTcParams q = p; q.m_tiles = 1;      // (an odd tile count switches the pair off)
             if (!conv_plan(q, CoutL, Cout, P_in, P_out, ksize, out_nchw_c, chan_sums, allow_stage, has_res)) return false;
@@ -983,6 +985,14 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
         cfg.attrs = &at; cfg.numAttrs = 1;
         const cudaError_t e = res ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, true>, mA0, mA1, mB, mOut, mRes, p)
                                   : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, true>, mA0, mA1, mB, mOut, mRes, p);
+        if (e == cudaErrorInvalidClusterSize || e == cudaErrorInvalidConfiguration || e == cudaErrorLaunchOutOfResources ||
+            e == cudaErrorNotSupported) {
+            // the launch was refused before anything ran: same layer again on the one-CTA kernel (still this library's tcgen05 path)
+            (void)cudaGetLastError();
+            g_pair_refused = 1;
+            fprintf(stderr, "hdiff_b200: cluster launch of the CTA-pair convolution refused (%s); using the one-CTA kernel\n", cudaGetErrorString(e));
+            return hd_conv_tc(in0, C0, in1, C1, P_in, w, bias, emb, emb_stride, res, out, Cout, P_out, N, H, W, ksize, out_nchw_c, chan_sums, stream);
+        }
         if (e != cudaSuccess) { hd_set_error(cudaGetErrorString(e)); return HD_ERR_CUDA; }
         HD_CHECK_LAUNCH();
         return HD_OK;
