@@ -61,13 +61,17 @@ PROTOTYPES = {
     "hd_sq_err_u8": [P, P, I, L, P, P],
     "hd_uiqm_workspace": [I],
     "hd_uiqm_u8": [P, I, I, I, P, L, P, P],
+    "hd_rgb2lab_u8": [P, L, P, P],
+    "hd_lab_tables_host": [P, P],
+    "hd_uciqe_workspace": [I],
+    "hd_uciqe_u8": [P, I, I, I, P, L, P, P],
     "hd_mha_supported": [I, I],
     "hd_mha_pack_heads": [P, P, I, I, I, I, I, F, P],
     "hd_mha_unpack_heads": [P, P, I, I, I, I, I, F, P],
     "hd_mha_fwd": [I, P, P, P, I, I, I, I, P],
     "hd_mha_bwd": [I, P, P, P, P, P, P, I, I, I, I, P],
 }
-NON_STATUS = {"hd_uiqm_workspace", "hd_gn_v2", "hd_mha_supported", "hd_conv_tc_supported", "hd_conv_tc_stats_staged", "hd_wgrad_tc_supported", "hd_attn_tc_supported", "hd_attn_bwd_tc_supported", "hd_attn_wide_tc_supported",
+NON_STATUS = {"hd_uiqm_workspace", "hd_uciqe_workspace", "hd_gn_v2", "hd_mha_supported", "hd_conv_tc_supported", "hd_conv_tc_stats_staged", "hd_wgrad_tc_supported", "hd_attn_tc_supported", "hd_attn_bwd_tc_supported", "hd_attn_wide_tc_supported",
               "hd_wgrad_tc_workspace"}
 
 # lab library only (include/hdiff_b200_lab.h): hardware probes and timing experiments, not part of the product ABI
@@ -101,7 +105,7 @@ def load():
     for name, args in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError here means the .so is stale
         fn.argtypes = args
-        fn.restype = L if name in ("hd_wgrad_tc_workspace", "hd_uiqm_workspace") else I
+        fn.restype = L if name in ("hd_wgrad_tc_workspace", "hd_uiqm_workspace", "hd_uciqe_workspace") else I
     _lib = lib
     return lib
 

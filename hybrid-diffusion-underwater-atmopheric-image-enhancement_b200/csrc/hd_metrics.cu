@@ -6,7 +6,9 @@
 //     imported at utils/rotinas.py:21);
 //   * hd_uiqm_u8: UIQM = c1 UICM + c2 UISM + c3 UIConM of metrics/metrics.py:77-299 (getUIQM) for 8-bit RGB images: per-pixel
 //     Python loops and sorts in the reference.  For 8-bit input R - G is an integer and (R + G) / 2 - B a half-integer, so the
-//     alpha-trimmed means come EXACTLY out of two histograms (no sort); Sobel / EME / UIConM are 8 x 8 block reductions.
+//     alpha-trimmed means come EXACTLY out of two histograms (no sort); Sobel / EME / UIConM are 8 x 8 block reductions;
+//   * hd_rgb2lab_u8: cv2.cvtColor(img, cv2.COLOR_RGB2LAB) for 8-bit images, BIT-EXACT (OpenCV's integer look-up-table path);
+//   * hd_uciqe_u8: UCIQE of metrics/metrics.py:40-76 (chroma deviation, luminance contrast out of a 65536-bin histogram, saturation).
 #include "hd_common.cuh"
 #include <math.h>
 
@@ -199,6 +201,161 @@ __global__ void uiqm_final_kernel(const UiqmWs* ws, int N, int H, int W, float* 
     out[4 * n + 1] = (float)uicm; out[4 * n + 2] = (float)uism; out[4 * n + 3] = (float)uiconm;
 }
 
+// ---- OpenCV's 8-bit RGB -> CIE Lab (cv2.cvtColor(img, cv2.COLOR_RGB2LAB), struct RGB2Lab_b in imgproc/src/color_lab.cpp) and UCIQE ----
+// Integer arithmetic on two look-up tables: the sRGB gamma curve scaled to 255 * 8 and the Lab f() curve scaled to 2^15 over 3072 arguments.
+// The tables are the published formulae evaluated in double; OpenCV initialises them in SINGLE precision, which lands on the other side of a
+// rounding boundary at exactly two arguments that any 8-bit colour can reach (49 and 628, both within 1.4e-4 of a half) — set below.  Pinned
+// over all 2^24 colours against cv2 itself by tests/test_metrics.py (oracle restatement on CPU, this kernel on the GPU).
+constexpr int kGammaTab = 256, kCbrtTab = 3072, kLabTab = kGammaTab + kCbrtTab;
+__device__ uint16_t g_lab_tab[kLabTab];
+
+static const uint16_t* lab_tables_host() {
+    static uint16_t tab[kLabTab];
+    static bool done = false;                     // idempotent: a second thread computes the same bytes
+    if (!done) {
+        for (int i = 0; i < kGammaTab; ++i) {
+            const double x = i / 255.0;
+            const double g = x <= 0.04045 ? x / 12.92 : pow((x + 0.055) / 1.055, 2.4);
+            tab[i] = (uint16_t)llrint(255.0 * 8.0 * g);
+        }
+        for (int i = 0; i < kCbrtTab; ++i) {
+            const double x = i / (255.0 * 8.0);
+            const double f = x < 216.0 / 24389.0 ? x * (841.0 / 108.0) + 16.0 / 116.0 : cbrt(x);
+            tab[kGammaTab + i] = (uint16_t)llrint(32768.0 * f);
+        }
+        tab[kGammaTab + 49] -= 1;
+        tab[kGammaTab + 628] += 1;
+        __atomic_store_n(&done, true, __ATOMIC_RELEASE);
+    }
+    return tab;
+}
+static int lab_tables_upload(cudaStream_t stream) {
+    static unsigned long long seen = 0;
+    if (!hd_seen_on_device(&seen)) {
+        if (cudaMemcpyToSymbolAsync(g_lab_tab, lab_tables_host(), sizeof(uint16_t) * kLabTab, 0, cudaMemcpyHostToDevice, stream) != cudaSuccess) return HD_ERR_CUDA;
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return HD_ERR_CUDA;      // once per device: later launches on ANY stream see the tables
+        hd_mark_on_device(&seen);
+    }
+    return HD_OK;
+}
+__device__ __forceinline__ void lab_tables_to_smem(uint16_t* tab) {
+    for (int i = threadIdx.x; i < kLabTab; i += blockDim.x) tab[i] = g_lab_tab[i];
+    __syncthreads();
+}
+// coefficients: round(4096 * sRGB->XYZ(D65) / white point), rows sum to 4096
+__device__ __forceinline__ void rgb2lab_px(const uint16_t* tab, int r, int g, int b, int* L, int* A, int* B) {
+    const uint16_t* cb = tab + kGammaTab;
+    const int R = tab[r], G = tab[g], Bc = tab[b];
+    const int fX = cb[(R * 1777 + G * 1541 + Bc * 778 + 2048) >> 12];
+    const int fY = cb[(R * 871 + G * 2929 + Bc * 296 + 2048) >> 12];
+    const int fZ = cb[(R * 73 + G * 448 + Bc * 3575 + 2048) >> 12];
+    const int l = (296 * fY - 1336935 + 16384) >> 15;                       // Lscale = (116*255+50)/100, Lshift = -((16*255*2^15+50)/100)
+    const int a = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
+    const int bb = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+    *L = min(max(l, 0), 255); *A = min(max(a, 0), 255); *B = min(max(bb, 0), 255);
+}
+__global__ void rgb2lab_u8_kernel(const uint8_t* __restrict__ rgb, int64_t npix, uint8_t* __restrict__ lab) {
+    __shared__ uint16_t tab[kLabTab];
+    lab_tables_to_smem(tab);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+        int L, A, B;
+        rgb2lab_px(tab, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], &L, &A, &B);
+        lab[3 * i] = (uint8_t)L; lab[3 * i + 1] = (uint8_t)A; lab[3 * i + 2] = (uint8_t)B;
+    }
+}
+
+// UCIQE (metrics/metrics.py:40-76): c1 * var_chr + c2 * con_lum + c3 * aver_sat on (L, a, b) / 255 in float64.  Every per-pixel quantity is
+// formed with the reference's own sequence of IEEE operations (explicit round-to-nearest intrinsics: no fused multiply-add), so only the
+// ORDER of the sums differs from numpy's.  The luminance takes at most 256 values, so np.histogram(lum, 65536) + cumsum is reproduced
+// exactly from a 256-bin integer histogram by the finalising thread.
+struct UciqeWs {                    // per image
+    double sum_chr, sum_sat, sum_dev;
+    unsigned int pad[2];
+    unsigned int hist[256];
+};
+__device__ __forceinline__ double uciqe_chroma(int A, int B) {
+    const double a = __ddiv_rn((double)A, 255.0), b = __ddiv_rn((double)B, 255.0);
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+}
+__device__ __forceinline__ double block_sum(double v, double* red) {      // result valid in thread 0
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    return t;
+}
+template <int kPass>
+__global__ void uciqe_pass_kernel(const uint8_t* __restrict__ img, int64_t npix, UciqeWs* ws) {
+    __shared__ uint16_t tab[kLabTab];
+    __shared__ unsigned int h[256];
+    __shared__ double red[8];
+    const int n = blockIdx.y;
+    if (kPass == 1) for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+    lab_tables_to_smem(tab);
+    const uint8_t* p = img + n * npix * 3;
+    const double aver_chr = kPass == 2 ? __ddiv_rn(ws[n].sum_chr, (double)npix) : 0.0;
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+        int L, A, B;
+        rgb2lab_px(tab, p[3 * i], p[3 * i + 1], p[3 * i + 2], &L, &A, &B);
+        const double chr = uciqe_chroma(A, B);
+        if (kPass == 1) {
+            const double lum = __ddiv_rn((double)L, 255.0);
+            s0 += chr;
+            s1 += __ddiv_rn(chr, __dsqrt_rn(__dadd_rn(__dmul_rn(chr, chr), __dmul_rn(lum, lum))));      // saturation
+            atomicAdd(&h[L], 1u);
+        } else {
+            const double q = __ddiv_rn(aver_chr, chr);
+            s0 += fabs(__dsub_rn(1.0, __dmul_rn(q, q)));
+        }
+    }
+    const double t0 = block_sum(s0, red);
+    if (kPass == 1) {
+        const double t1 = block_sum(s1, red);
+        if (threadIdx.x == 0) { atomicAdd(&ws[n].sum_chr, t0); atomicAdd(&ws[n].sum_sat, t1); }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) if (h[i]) atomicAdd(&ws[n].hist[i], h[i]);
+    } else if (threadIdx.x == 0) {
+        atomicAdd(&ws[n].sum_dev, t0);
+    }
+}
+__global__ void uciqe_final_kernel(const UciqeWs* ws, int N, int64_t npix, double* out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const unsigned int* h = ws[n].hist;
+    const double K = (double)npix;
+    const double var_chr = __dsqrt_rn(__ddiv_rn(ws[n].sum_dev, K)), aver_sat = __ddiv_rn(ws[n].sum_sat, K);
+    // np.histogram(lum, 65536): uniform bins over [min, max] (an empty range is widened by 0.5 on both sides), edge(i) = i * step + first
+    // (np.linspace), index = trunc((v - first) / (last - first) * 65536) corrected against the computed edges
+    constexpr int NB = 65536;
+    int kmin = 0, kmax = 255;
+    while (kmin < 255 && h[kmin] == 0) ++kmin;
+    while (kmax > 0 && h[kmax] == 0) --kmax;
+    double first = __ddiv_rn((double)kmin, 255.0), last = __ddiv_rn((double)kmax, 255.0);
+    if (first == last) { first = __dsub_rn(first, 0.5); last = __dadd_rn(last, 0.5); }
+    const double denom = __dsub_rn(last, first), step = __ddiv_rn(denom, (double)NB);
+    auto edge = [&](int i) { return i == NB ? last : __dadd_rn(__dmul_rn((double)i, step), first); };
+    long long cum = 0; int ilow = -1, ihigh = -1;
+    for (int k = kmin; k <= kmax; ++k) {
+        if (h[k] == 0) continue;
+        const double v = __ddiv_rn((double)k, 255.0);
+        int idx = (int)__dmul_rn(__ddiv_rn(__dsub_rn(v, first), denom), (double)NB);
+        if (idx == NB) --idx;
+        if (v < edge(idx)) --idx;
+        if (v >= edge(idx + 1) && idx != NB - 1) ++idx;
+        cum += h[k];
+        const double cdf = __ddiv_rn((double)cum, K);
+        if (ilow < 0 && cdf > 0.0100) ilow = idx;
+        if (ihigh < 0 && cdf >= 0.9900) ihigh = idx;
+    }
+    const double con_lum = __dsub_rn(__ddiv_rn((double)(ihigh - 1), (double)(NB - 1)), __ddiv_rn((double)(ilow - 1), (double)(NB - 1)));
+    // coe_metric[0] * var_chr + coe_metric[1] * con_lum + coe_metric[2] * aver_sat, left to right
+    out[4 * n] = __dadd_rn(__dadd_rn(__dmul_rn(0.4680, var_chr), __dmul_rn(0.2745, con_lum)), __dmul_rn(0.2576, aver_sat));
+    out[4 * n + 1] = var_chr; out[4 * n + 2] = con_lum; out[4 * n + 3] = aver_sat;
+}
+
 }  // namespace
 
 extern "C" int hd_resize_bilinear_u8(const void* src, int N, int SH, int SW, int C, void* dst, int DH, int DW, int chw, cudaStream_t stream) {
@@ -234,6 +391,39 @@ extern "C" int hd_uiqm_u8(const void* img, int N, int H, int W, void* workspace,
     int bb = (nblk + 127) / 128; if (bb > 64) bb = 64;
     uiqm_block_kernel<<<dim3(bb, N), 128, 0, stream>>>((const uint8_t*)img, H, W, ws);
     uiqm_final_kernel<<<(N + 63) / 64, 64, 0, stream>>>(ws, N, H, W, out);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+
+// The two look-up tables of the Lab conversion, host memory (no GPU needed): gamma[256], cbrt[3072]
+extern "C" int hd_lab_tables_host(uint16_t* gamma, uint16_t* cbrt_tab) {
+    HD_REQUIRE(gamma && cbrt_tab);
+    const uint16_t* t = lab_tables_host();
+    for (int i = 0; i < kGammaTab; ++i) gamma[i] = t[i];
+    for (int i = 0; i < kCbrtTab; ++i) cbrt_tab[i] = t[kGammaTab + i];
+    return HD_OK;
+}
+// rgb, lab: [npix][3] uint8; bit-exact with cv2.cvtColor(img, cv2.COLOR_RGB2LAB)
+extern "C" int hd_rgb2lab_u8(const void* rgb, int64_t npix, void* lab, cudaStream_t stream) {
+    HD_REQUIRE(rgb && lab && npix > 0);
+    if (int rc = lab_tables_upload(stream)) return rc;
+    int64_t blocks = (npix + 255) / 256; if (blocks > (int64_t)hd_num_sms() * 8) blocks = (int64_t)hd_num_sms() * 8;
+    rgb2lab_u8_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const uint8_t*)rgb, npix, (uint8_t*)lab);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+extern "C" int64_t hd_uciqe_workspace(int N) { return (int64_t)N * (int64_t)sizeof(UciqeWs); }
+// img: [N][H][W][3] uint8 RGB; out: [N][4] float64 = (UCIQE, var_chr, con_lum, aver_sat) of metrics/metrics.py:40-76
+extern "C" int hd_uciqe_u8(const void* img, int N, int H, int W, void* workspace, int64_t ws_bytes, double* out, cudaStream_t stream) {
+    HD_REQUIRE(img && workspace && out && N > 0 && H > 0 && W > 0 && ws_bytes >= hd_uciqe_workspace(N));
+    if (int rc = lab_tables_upload(stream)) return rc;
+    UciqeWs* ws = (UciqeWs*)workspace;
+    if (cudaMemsetAsync(ws, 0, (size_t)hd_uciqe_workspace(N), stream) != cudaSuccess) return HD_ERR_CUDA;
+    const int64_t npix = (int64_t)H * W;
+    int bx = (int)((npix + 256 * 8 - 1) / (256 * 8)); if (bx > 64) bx = 64;
+    uciqe_pass_kernel<1><<<dim3(bx, N), 256, 0, stream>>>((const uint8_t*)img, npix, ws);
+    uciqe_pass_kernel<2><<<dim3(bx, N), 256, 0, stream>>>((const uint8_t*)img, npix, ws);
+    uciqe_final_kernel<<<(N + 63) / 64, 64, 0, stream>>>(ws, N, npix, out);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }

@@ -4,7 +4,9 @@ Reference followed (paths relative to the reference repository):
   resize_u8      albumentations A.Resize(256, 256) [= cv2.resize(..., INTER_LINEAR)] + ToTensorV2, utils/utils.py:318-323,441-462
   psnr_u8        skimage.metrics.peak_signal_noise_ratio as imported at utils/rotinas.py:21 (data_range 255)
   uiqm_u8        metrics/metrics.py:77-299 (getUIQM = 0.0282 UICM + 0.2953 UISM + 3.5753 UIConM)
-All three call the C-ABI library (csrc/hd_metrics.cu); there is no CPU fallback."""
+  rgb2lab_u8     cv2.cvtColor(img, cv2.COLOR_RGB2LAB) on 8-bit images, metrics/metrics.py:43
+  uciqe_u8       metrics/metrics.py:40-76 (uciqe(nargin=1, loc=img) = 0.4680 var_chr + 0.2745 con_lum + 0.2576 aver_sat)
+All of them call the C-ABI library (csrc/hd_metrics.cu); there is no CPU fallback."""
 from __future__ import annotations
 
 import torch
@@ -48,4 +50,26 @@ def uiqm_u8(images):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=images.device)
     out = torch.empty((N, 4), dtype=torch.float32, device=images.device)
     _lib.check(lib.hd_uiqm_u8(_p(images), N, H, W, _p(ws), nbytes, _p(out), _stream()), "hd_uiqm_u8")
+    return out
+
+
+def rgb2lab_u8(images):
+    """images: uint8 RGB [..., 3] -> uint8 Lab [..., 3], bit-exact with cv2.cvtColor(img, cv2.COLOR_RGB2LAB)"""
+    _check_u8(images, images.dim())
+    assert images.shape[-1] == 3
+    out = torch.empty_like(images)
+    _lib.check(_lib.load().hd_rgb2lab_u8(_p(images), images.numel() // 3, _p(out), _stream()), "hd_rgb2lab_u8")
+    return out
+
+
+def uciqe_u8(images):
+    """images: uint8 RGB [N, H, W, 3] -> float64 [N, 4] = (UCIQE, var_chr, con_lum, aver_sat) per image"""
+    _check_u8(images, 4)
+    N, H, W, C = images.shape
+    assert C == 3
+    lib = _lib.load()
+    nbytes = int(lib.hd_uciqe_workspace(N))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=images.device)
+    out = torch.empty((N, 4), dtype=torch.float64, device=images.device)
+    _lib.check(lib.hd_uciqe_u8(_p(images), N, H, W, _p(ws), nbytes, _p(out), _stream()), "hd_uciqe_u8")
     return out

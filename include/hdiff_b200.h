@@ -110,6 +110,13 @@ int hd_resize_bilinear_u8(const void* src, int N, int SH, int SW, int C, void* d
 int hd_sq_err_u8(const void* a, const void* b, int N, int64_t per_image, double* sq_err, hd_stream_t stream);
 int64_t hd_uiqm_workspace(int N);
 int hd_uiqm_u8(const void* img, int N, int H, int W, void* workspace, int64_t ws_bytes, float* out, hd_stream_t stream);
+/*      hd_rgb2lab_u8: cv2.cvtColor(img, cv2.COLOR_RGB2LAB) on 8-bit pixels, bit-exact, [npix][3] -> [npix][3] (metrics/metrics.py:43).
+ *      hd_lab_tables_host: the conversion's two look-up tables written to HOST memory (gamma[256], cbrt[3072]); needs no GPU.
+ *      hd_uciqe_u8: out[n] = (UCIQE, var_chr, con_lum, aver_sat) in float64 of metrics/metrics.py:40-76 (uciqe(nargin=1, loc=img)). */
+int hd_rgb2lab_u8(const void* rgb, int64_t npix, void* lab, hd_stream_t stream);
+int hd_lab_tables_host(uint16_t* gamma, uint16_t* cbrt_tab);
+int64_t hd_uciqe_workspace(int N);
+int hd_uciqe_u8(const void* img, int N, int H, int W, void* workspace, int64_t ws_bytes, double* out, hd_stream_t stream);
 
 /* ---- GroupNorm(32) + Swish (+ Dropout): ModelCondition.py:128-129,141-143,95,249-250.  Two-source input
  *      (C0 | C1 channels) fuses torch.cat :271 into the normalisation.  sums/gsums = [N][G][2] fp64. ---- */

@@ -6,6 +6,15 @@ metric kernels of csrc/hd_metrics.cu.
                        fixed-point weights `cvRound(w * 2048)`, horizontal pass in int, vertical pass
                        `(((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2`).  Pinned bit-for-bit against cv2.resize
                        itself (opencv-python 4.13 in this image) by tests/test_metrics.py.
+  rgb2lab_u8           numpy restatement of OpenCV's 8-bit RGB -> Lab (cv2.cvtColor(img, cv2.COLOR_RGB2LAB), the call at
+                       metrics/metrics.py:43; algorithm in the third-party dependency opencv-python, `RGB2Lab_b` of
+                       imgproc/src/color_lab.cpp: sRGB gamma table scaled by 255 * 8, 12-bit XYZ coefficients divided by the D65
+                       white point, Lab f() table scaled by 2^15, `CV_DESCALE` roundings).  Pinned bit-for-bit against cv2 itself
+                       over ALL 2^24 colours by tests/test_metrics.py.
+  uciqe_restated       the algorithm of csrc/hd_metrics.cu's UCIQE kernels in numpy float64: per-pixel terms as in the reference,
+                       np.histogram(lum, 65536) + cumsum reproduced from a 256-bin integer histogram of L.  Pinned against the
+                       reference's own uciqe by tests/test_metrics.py.
+  reference_uciqe      the reference's OWN uciqe (metrics/metrics.py:40-76), cut out of the unmodified file by AST.
   reference_uiqm       the reference's OWN getUIQM (metrics/metrics.py:77-299), cut out of the unmodified file by AST (the module
                        imports torchvision's Inception and skimage at the top and cannot be imported whole here).
 """
@@ -47,7 +56,96 @@ def resize_bilinear_u8(src, dh, dw):
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
+def lab_tables():
+    """-> (gamma[256], cbrt[3072]) int64.  The published formulae in float64; OpenCV fills its tables in single precision, which falls on
+    the other side of a rounding boundary at two reachable arguments (49, 628)."""
+    x = np.arange(256) / 255.0
+    gamma = np.rint(255.0 * 8 * np.where(x <= 0.04045, x / 12.92, ((x + 0.055) / 1.055) ** 2.4)).astype(np.int64)
+    y = np.arange(3072) / (255.0 * 8)
+    cb = np.rint(32768 * np.where(y < 216 / 24389, y * (841 / 108) + 16 / 116, np.cbrt(y))).astype(np.int64)
+    cb[49] -= 1
+    cb[628] += 1
+    return gamma, cb
+
+
+def rgb2lab_u8(img):
+    """img: uint8 RGB [..., 3] -> uint8 Lab [..., 3]"""
+    gamma, cb = lab_tables()
+    m = np.array([[0.412453, 0.357580, 0.180423], [0.212671, 0.715160, 0.072169], [0.019334, 0.119193, 0.950227]])
+    c = np.rint(4096 * m / np.array([0.950456, 1.0, 1.088754])[:, None]).astype(np.int64)
+
+    def descale(v, n):
+        return (v + (1 << (n - 1))) >> n
+
+    r, g, b = gamma[img[..., 0]], gamma[img[..., 1]], gamma[img[..., 2]]
+    fx = cb[descale(r * c[0, 0] + g * c[0, 1] + b * c[0, 2], 12)]
+    fy = cb[descale(r * c[1, 0] + g * c[1, 1] + b * c[1, 2], 12)]
+    fz = cb[descale(r * c[2, 0] + g * c[2, 1] + b * c[2, 2], 12)]
+    lscale, lshift = (116 * 255 + 50) // 100, -((16 * 255 * (1 << 15) + 50) // 100)
+    out = np.stack([descale(lscale * fy + lshift, 15), descale(500 * (fx - fy) + 128 * (1 << 15), 15),
+                    descale(200 * (fy - fz) + 128 * (1 << 15), 15)], -1)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def uciqe_restated(img):
+    """img: HWC uint8 RGB -> (UCIQE, var_chr, con_lum, aver_sat), following metrics/metrics.py:40-76"""
+    lab = rgb2lab_u8(img)
+    f = np.float64
+    with np.errstate(all="ignore"):
+        lum, a, b = lab[..., 0] / f(255), lab[..., 1] / f(255), lab[..., 2] / f(255)
+        chroma = np.sqrt(a * a + b * b)
+        aver_sat = np.mean(chroma / np.sqrt(chroma * chroma + lum * lum))
+        var_chr = np.sqrt(np.mean(np.abs(1 - np.square(np.mean(chroma) / chroma))))
+    h = np.bincount(lab[..., 0].ravel(), minlength=256)
+    nb = 65536
+    occ = np.nonzero(h)[0]
+    first, last = f(occ[0]) / f(255), f(occ[-1]) / f(255)
+    if first == last:
+        first, last = first - 0.5, last + 0.5
+    denom = last - first
+    step = denom / f(nb)
+
+    def edge(i):
+        return last if i == nb else f(i) * step + first
+
+    total, cum, ilow, ihigh = int(h.sum()), 0, None, None
+    for k in occ:
+        v = f(k) / f(255)
+        idx = int(((v - first) / denom) * f(nb))
+        if idx == nb:
+            idx -= 1
+        if v < edge(idx):
+            idx -= 1
+        if v >= edge(idx + 1) and idx != nb - 1:
+            idx += 1
+        cum += int(h[k])
+        cdf = f(cum) / f(total)
+        if ilow is None and cdf > 0.0100:
+            ilow = idx
+        if ihigh is None and cdf >= 0.9900:
+            ihigh = idx
+    con_lum = f(ihigh - 1) / f(nb - 1) - f(ilow - 1) / f(nb - 1)
+    return 0.4680 * var_chr + 0.2745 * con_lum + 0.2576 * aver_sat, var_chr, con_lum, aver_sat
+
+
 _cache = {}
+
+
+def reference_uciqe():
+    """-> the reference's uciqe(nargin, loc) (loc: HWC uint8 RGB image), executed from the unmodified source (needs cv2)"""
+    if "uciqe" not in _cache:
+        import ast
+        import cv2
+        from . import ref_loader
+        path = os.path.join(ref_loader.REF_ROOT, "metrics", "metrics.py")
+        with open(path, "r") as f:
+            tree = ast.parse(f.read())
+        keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "uciqe"][:1]
+        assert keep
+        ns = {"np": np, "cv2": cv2}
+        exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+        _cache["uciqe"] = ns["uciqe"]
+    return _cache["uciqe"]
 
 
 def reference_uiqm():

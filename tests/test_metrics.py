@@ -69,3 +69,81 @@ def test_uiqm_kernel_vs_reference_getUIQM():
         x = img.astype(np.float32)
         want = (ns["getUIQM"](img), ns["_uicm"](x), ns["_uism"](x), ns["_uiconm"](x, 8))
         assert np.allclose(got[i], want, rtol=2e-4, atol=1e-5), (i, got[i], want)
+
+
+def _all_colours():
+    v = np.arange(256, dtype=np.uint8)
+    return np.ascontiguousarray(np.stack(np.meshgrid(v, v, v, indexing="ij"), -1).reshape(4096, 4096, 3))
+
+
+def test_rgb2lab_restatement_is_bit_exact_with_cv2_on_all_colours():
+    allc = _all_colours()
+    want = cv2.cvtColor(allc, cv2.COLOR_RGB2LAB)
+    assert np.array_equal(ref_metrics.rgb2lab_u8(allc), want)
+
+
+def test_library_lab_tables_equal_the_oracle_tables():
+    """host-only entry point (no GPU): the tables the kernels use are the ones pinned above"""
+    import ctypes
+    from hdiff_b200 import _lib
+    gamma = (ctypes.c_uint16 * 256)()
+    cb = (ctypes.c_uint16 * 3072)()
+    assert _lib.load().hd_lab_tables_host(gamma, cb) == 0
+    g, c = ref_metrics.lab_tables()
+    assert np.array_equal(np.frombuffer(gamma, np.uint16), g) and np.array_equal(np.frombuffer(cb, np.uint16), c)
+
+
+@pytest.mark.gpu
+def test_rgb2lab_kernel_is_bit_exact_with_cv2_on_all_colours():
+    from hdiff_b200 import metrics
+    allc = _all_colours()
+    want = cv2.cvtColor(allc, cv2.COLOR_RGB2LAB)
+    got = metrics.rgb2lab_u8(torch.from_numpy(allc).cuda()).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def _uciqe_images():
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:120, 0:160]
+    smooth = np.stack([127 + 100 * np.sin(xx / 11.0 + c) * np.cos(yy / 8.0 - c) for c in range(3)], -1)
+    water = np.clip(smooth * np.array([0.25, 0.6, 0.8]) + np.array([10, 60, 90]) + rng.normal(0, 6, smooth.shape), 0, 255)
+    return np.stack([np.clip(smooth + rng.normal(0, 12, smooth.shape), 0, 255).astype(np.uint8),
+                     rng.integers(0, 256, (120, 160, 3), dtype=np.uint8),
+                     water.astype(np.uint8),
+                     np.full((120, 160, 3), (40, 90, 160), dtype=np.uint8)])           # one colour: the empty-range histogram branch
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference sources not present")
+def test_uciqe_restatement_vs_reference_uciqe():
+    """the kernels' algorithm (256-bin histogram instead of np.histogram's 65536 bins) against the reference's own function"""
+    uciqe = ref_metrics.reference_uciqe()
+    rng = np.random.default_rng(6)
+    extra = [np.clip(rng.normal(rng.integers(30, 220), rng.integers(1, 60), (48, 64, 3)), 0, 255).astype(np.uint8) for _ in range(12)]
+    for img in list(_uciqe_images()) + extra:
+        with np.errstate(all="ignore"):
+            want = uciqe(nargin=1, loc=img)
+        got = ref_metrics.uciqe_restated(img)
+        assert abs(got[0] - want) <= 1e-14 * abs(want), (got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not ref_loader.available(), reason="reference sources not present")
+def test_uciqe_kernel_vs_reference_uciqe():
+    """The reference's own uciqe (cv2 Lab conversion, numpy float64, np.histogram with 65536 bins): the per-pixel arithmetic and the
+    histogram bins are reproduced exactly, only the order of the float64 sums differs."""
+    from hdiff_b200 import metrics
+    uciqe = ref_metrics.reference_uciqe()
+    imgs = _uciqe_images()
+    got = metrics.uciqe_u8(torch.from_numpy(imgs).cuda()).cpu().numpy()
+    for i, img in enumerate(imgs):
+        with np.errstate(all="ignore"):
+            want = uciqe(nargin=1, loc=img)
+        # image 3 is one colour: var_chr = sqrt(mean |1 - (mean(chroma) / chroma)^2|) is the square root of pure rounding noise there
+        # (1e-16 -> 1e-8 in either implementation), everywhere else the sums agree to the last few bits
+        tol = dict(rtol=1e-11, atol=0) if i != 3 else dict(rtol=0, atol=1e-7)
+        assert np.isclose(got[i, 0], want, **tol), (i, got[i], want)
+        lab = cv2.cvtColor(img, cv2.COLOR_RGB2LAB) / 255
+        chr_ = np.sqrt(lab[..., 1] ** 2 + lab[..., 2] ** 2)
+        assert np.isclose(got[i, 3], np.mean(chr_ / np.sqrt(chr_ ** 2 + lab[..., 0] ** 2)), rtol=1e-12)
+        assert np.isclose(got[i, 1], np.sqrt(np.mean(abs(1 - np.square(np.mean(chr_) / chr_)))), **tol)
+        assert np.isclose(got[i, 2], ref_metrics.uciqe_restated(img)[2], rtol=0, atol=1e-15), (i, got[i, 2])     # the histogram bins are exact
