@@ -452,10 +452,16 @@ def run_ours(args):
     prof, ops.prof = ops.prof, None
 
     fam = {}
-    for name, lst in prof.items():
-        t = sum(a.elapsed_time(b) for a, b, _ in lst)
-        fam[name] = {"ms": t, "work": sum(w for _, _, w in lst), "launches": len(lst)}
     peaks = _peaks()
+    for name, lst in prof.items():
+        t = sum(r[0].elapsed_time(r[1]) for r in lst)
+        fam[name] = {"ms": t, "work": sum(r[2] for r in lst), "launches": len(lst)}
+        if any(len(r) > 3 for r in lst):
+            # per launch, the roofline that BINDS it: the longer of (algorithmic FLOPs / sustained tensor peak) and (compulsory bytes / copy
+            # bandwidth).  The 1x1 convolutions and the 64-channel layers at 256x256 move more bytes than their FLOPs can hide.
+            lb = [(r[2] / (peaks["bf16_tflops_sustained"] * 1e12), (r[3] if len(r) > 3 else 0.0) / (peaks["hbm_gbs"] * 1e9)) for r in lst]
+            fam[name]["bound_ms"] = 1e3 * sum(max(a, b) for a, b in lb)
+            fam[name]["hbm_bound_launches"] = sum(1 for a, b in lb if b > a)
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
@@ -469,6 +475,9 @@ def run_ours(args):
         peak = peaks["bf16_tflops_sustained"] if tensor else peaks["hbm_gbs"]
         fam_out[name] = {"ms_per_step": f["ms"] / n_prof, "launches_per_step": f["launches"] / n_prof,
                          "achieved": ach, "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak}
+        if "bound_ms" in f:
+            fam_out[name]["frac_of_binding_roofline"] = f["bound_ms"] / f["ms"] if f["ms"] > 0 else 0.0
+            fam_out[name]["hbm_bound_launches_per_step"] = f["hbm_bound_launches"] / n_prof
         if roof is None:
             roof = {"kernel": name, "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak,

@@ -49,12 +49,18 @@ class CudaOps:
         e.record()
         return e
 
-    def _t1(self, e0, family, work):
+    def _t1(self, e0, family, work, hbm_bytes=None):
+        """`work`: algorithmic FLOPs (tensor families) or compulsory bytes (HBM families) of the launch; `hbm_bytes`: for a tensor-family
+        launch, its compulsory HBM bytes as well (every operand once), so that bench.py can say which roofline binds that launch."""
         if e0 is None:
             return
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        self.prof.setdefault(family, []).append((e0, e1, work))
+        self.prof.setdefault(family, []).append((e0, e1, work) if hbm_bytes is None else (e0, e1, work, hbm_bytes))
+
+    @staticmethod
+    def _nbytes(*tensors):
+        return float(sum(t.numel() * t.element_size() for t in tensors if t is not None))
 
     # ---- convolution family -------------------------------------------------------------
     def conv(self, x0, x1, P_in, w, bias, emb, res, out, P_out, N, H, W, k, in_nchw=False, out_nchw=False, alg_frac=1.0,
@@ -81,7 +87,7 @@ class CudaOps:
             _lib.check(rc, "hd_conv_tc")
             self.launches += 1
             self.tc_launches += 1
-            self._t1(e0, "conv_tc", flops)
+            self._t1(e0, "conv_tc", flops, self._nbytes(x0, x1, w, res, out) if e0 is not None else None)
             return True if chan_sums is not None else None      # True: the per-channel statistics were produced
         if self.use_tc and dt == BF16 and not quiet:
             _warn_cuda_core("conv", f"C={C0}+{C1} P_in={P_in} Cout={Cout} P_out={P_out} H={H} W={W} k={k}")
@@ -112,7 +118,7 @@ class CudaOps:
             _lib.check(rc, "hd_wgrad_tc")
             self.launches += 2
             self.tc_launches += 1
-            self._t1(e0, "wgrad_tc", flops)
+            self._t1(e0, "wgrad_tc", flops, self._nbytes(x0, x1, dy, dw) if e0 is not None else None)
             return
         if self.use_tc and dt == BF16 and not quiet:
             _warn_cuda_core("wgrad", f"C={C0}+{C1} P_in={P_in} Cdy={Cdy} P_dy={P_dy} H={H} W={W} k={k}")

@@ -13,6 +13,9 @@ from hdiff_b200.diffusion.Diffusion import GaussianDiffusionTrainer  # noqa: E40
 import hdiff_b200.ops as hops  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) as _f:
+    _pk = json.load(_f)
+PEAK_TFLOPS, PEAK_GBS = _pk["bf16_tflops_sustained"], _pk["hbm_gbs"]      # GFLOP / (TFLOP/s) = ms, MB / (GB/s) = ms
 dev = torch.device("cuda")
 torch.manual_seed(0)
 net = UNet(T=1000, ch=64, ch_mult=[1, 2, 2, 2], attn=[1], num_res_blocks=2, dropout=0.1).to(dev)
@@ -53,11 +56,20 @@ out = {}
 for fam in shapes:
     agg = collections.OrderedDict()
     assert len(shapes[fam]) == len(prof[fam]), (fam, len(shapes[fam]), len(prof[fam]))
-    for s, (a, b, w) in zip(shapes[fam], prof[fam]):
-        e = agg.setdefault(s, {"n": 0, "ms": 0.0, "gflop": 0.0})
-        e["n"] += 1; e["ms"] += a.elapsed_time(b); e["gflop"] += w / 1e9
+    for s, r in zip(shapes[fam], prof[fam]):
+        a, b, w = r[:3]
+        e = agg.setdefault(s, {"n": 0, "ms": 0.0, "gflop": 0.0, "mbyte": 0.0})
+        e["n"] += 1; e["ms"] += a.elapsed_time(b); e["gflop"] += w / 1e9; e["mbyte"] += (r[3] if len(r) > 3 else 0.0) / 1e6
+    bound_total = 0.0
     for e in agg.values():
-        e["tflops"] = round(e["gflop"] / e["ms"], 1); e["ms"] = round(e["ms"], 3); e["gflop"] = round(e["gflop"], 1)
+        # the roofline that binds this shape: the longer of FLOPs / sustained tensor peak and compulsory bytes / copy bandwidth
+        t_tensor, t_hbm = e["gflop"] / PEAK_TFLOPS, e["mbyte"] / PEAK_GBS          # both in ms
+        e["bound"] = "hbm" if t_hbm > t_tensor else "tensor"
+        e["frac_of_binding_roofline"] = round(max(t_tensor, t_hbm) / e["ms"], 3)
+        bound_total += max(t_tensor, t_hbm)
+        e["tflops"] = round(e["gflop"] / e["ms"], 1); e["gbs"] = round(e["mbyte"] / e["ms"], 1)
+        e["ms"] = round(e["ms"], 3); e["gflop"] = round(e["gflop"], 1); e["mbyte"] = round(e["mbyte"], 1)
+    out[fam + "_frac_of_binding_roofline"] = round(bound_total / sum(e["ms"] for e in agg.values()), 3)
     out[fam] = dict(sorted(agg.items(), key=lambda kv: -kv[1]["ms"]))
     out[fam + "_total_ms"] = round(sum(e["ms"] for e in agg.values()), 3)
 print(json.dumps(out, indent=1))

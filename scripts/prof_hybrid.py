@@ -50,7 +50,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     total = e0.elapsed_time(e1)
-    fam = {k: (sum(a.elapsed_time(b) for a, b, _ in v), len(v), sum(w for _, _, w in v)) for k, v in ops.prof.items()}
+    fam = {k: (sum(r[0].elapsed_time(r[1]) for r in v), len(v), sum(r[2] for r in v)) for k, v in ops.prof.items()}
     ops.prof = None
     print(f"step with events {total:.2f} ms; families sum {sum(v[0] for v in fam.values()):.2f} ms")
     for k, (ms, n, w) in sorted(fam.items(), key=lambda kv: -kv[1][0]):

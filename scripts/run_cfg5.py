@@ -39,7 +39,7 @@ ops.prof = {}
 opt.zero_grad(); loss = tr(x).sum() / 1000.; loss.backward(); opt.step()
 torch.cuda.synchronize()
 prof, ops.prof = ops.prof, None
-fam = {k: {"launches": len(v), "ms": round(sum(a.elapsed_time(b) for a, b, _ in v), 3)} for k, v in prof.items()}
+fam = {k: {"launches": len(v), "ms": round(sum(r[0].elapsed_time(r[1]) for r in v), 3)} for k, v in prof.items()}
 print(json.dumps({"config": "cfg5 uncond UNet ch=128 [1,1,2,2,4] attn=[3,4] nrb=2, 512x512", "params": nparam, "batch": B,
                   "ms_per_step_median": sorted(ts[1:])[len(ts[1:]) // 2] * 1e3, "images_per_s": B / sorted(ts[1:])[len(ts[1:]) // 2],
                   "losses": losses, "finite": all(l == l and abs(l) < 1e9 for l in losses),
