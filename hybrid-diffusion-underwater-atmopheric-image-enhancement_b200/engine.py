@@ -593,7 +593,7 @@ class UNetBase(nn.Module):
     @staticmethod
     def _side_stream(st, like):
         """The stream the weight-gradient kernels run on (None: the current stream)."""
-        if not (WGRAD_SIDE_STREAM and like.is_cuda):
+        if not (WGRAD_SIDE_STREAM and like.is_cuda) or getattr(_ops.get(), "prof", None) is not None:      # per-launch timing: everything on one stream
             return None
         if getattr(st, "side", None) is None:
             st.side = torch.cuda.Stream(device=like.device)
