@@ -87,6 +87,8 @@ struct ConvTcParams {
     int a_slot, a_tx;                // shared-memory bytes reserved for / transferred into the A part of a stage
     double* chan_sums;               // optional [N][Cout][2]: per-image, per-channel sum / sum of squares of the STORED output
                                      // (the GroupNorm statistics of the next layer, without another pass over the tensor)
+    int stage_bufs;                  // staging buffers of that epilogue: 2, or 4 (tensor stores of up to three earlier blocks may still be
+                                     // reading shared memory while a block is staged; never with a residual, whose prefetch protocol alternates two)
     int stage_out;                   // epilogue stages 64-channel blocks of the tile in shared memory (128-byte swizzle) and writes them
                                      // with TMA tensor stores: whole 128-byte lines instead of 32-byte pieces per thread
     int wres, kb_w;                  // wres: the whole packed weight matrix (n_tiles x kb_w blocks of [NT][64] bf16) is loaded ONCE per CTA
@@ -120,7 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int stage_bytes = p.a_slot + (p.wres ? 0 : (p.txm ? 3 : 1) * b_bytes);
     const int stage_tx = p.a_tx + (p.wres ? 0 : (p.txm ? 3 : 1) * b_bytes);
     uint8_t* stage_buf = smem + (size_t)p.stages * stage_bytes;                  // [2][128 pixels][64 channels] bf16 when p.stage_out
-    uint8_t* wres_buf = stage_buf + (p.stage_out ? 2 * kABytes : 0);             // [n_tiles][kb_w][NT][64] bf16 when p.wres
+    uint8_t* wres_buf = stage_buf + (p.stage_out ? p.stage_bufs * kABytes : 0);             // [n_tiles][kb_w][NT][64] bf16 when p.wres
     uint64_t* bars = reinterpret_cast<uint64_t*>(wres_buf + (p.wres ? (size_t)p.n_tiles * p.kb_w * b_bytes : 0));
     uint64_t* full = bars;                       // [stages]
     uint64_t* empty = bars + kMaxStages;         // [stages]
@@ -416,7 +418,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int etid = (warp - 2) * 32 + lane;     // 0 .. 255 among the epilogue threads
         const int ty = row / p.TW, tx = row % p.TW;
         int it = 0;
-        uint32_t sb = 0;                             // staged 64-channel blocks so far (p.stage_out): buffer = sb & 1
+        uint32_t sb = 0;                             // staged 64-channel blocks so far (p.stage_out): buffer = sb % p.stage_bufs
         // staged epilogue + residual: the residual block is brought into the staging buffer by TMA one block ahead (issued
         // by thread 0 right after the barrier that frees the buffer) and the output is formed in place over it
         auto res_load = [&](int tl, int blk, uint32_t buf) {
@@ -599,12 +601,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         __syncwarp();
                         if (lane == 0) release_acc(acc);
                     }
-                    uint8_t* sbuf = stage_buf + (sb & 1) * kABytes;
+                    uint8_t* sbuf = stage_buf + (sb & (uint32_t)(p.stage_bufs - 1)) * kABytes;
                     if (kRes) mbar_wait(&res_full[sb & 1], (sb >> 1) & 1);
                     stage_emit(va, c, sbuf + row * 128, half * 2, nullptr);
                     stage_emit(vb, c + 32, sbuf + row * 128, half * 2 + 4, nullptr);
                     fence_proxy_async_smem();
-                    if (etid == 0) bulk_wait_group_read0();
+                    if (etid == 0) { if (p.stage_bufs == 4) bulk_wait_group_read2(); else bulk_wait_group_read0(); }
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (etid == 0) {
                         // logical channel block j0 of the tile -> (channel, parity row) of the output view (P_out == 2: the four
@@ -801,11 +803,14 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
         // HDIFF_CONV_PAIR=0 switches the mode off.
         static const int pair_env = getenv("HDIFF_CONV_PAIR") ? atoi(getenv("HDIFF_CONV_PAIR")) : 1;
         const bool pair_shape = p.NT == 64 || p.NT == 128 || p.NT == 256;
+        // staging buffers: HDIFF_CONV_STAGE_BUFS=4 gives the 1x1 layers four (44: every staged layer without a residual)
+        static const int sbufs_env = getenv("HDIFF_CONV_STAGE_BUFS") ? atoi(getenv("HDIFF_CONV_STAGE_BUFS")) : 2;
+        const int nbufs = !has_res && ((sbufs_env == 4 && ksize == 1) || sbufs_env == 44) ? 4 : 2;
         const bool pair = pair_env > 0 && !g_pair_refused && ksize == 3 && pair_shape && out_nchw_c == 0 && p.m_tiles % 2 == 0 && p.m_tiles >= 2;
         const int b_rows = pair ? p.NT / 2 : p.NT;
         auto stages_of = [&](bool txm, bool wres, bool stage) {
             const int sbytes = (txm ? txm_a_slot : kABytes) + (wres ? 0 : (txm ? 3 : 1) * b_rows * 128);
-            const long long avail = budget - (stage ? 2 * kABytes : 0) - (wres ? wbytes : 0);
+            const long long avail = budget - (stage ? nbufs * kABytes : 0) - (wres ? wbytes : 0);
             return avail <= 0 ? 0 : (int)(avail / sbytes);
         };
         bool txm = false, wres = false, stage = false, found = false;
@@ -814,7 +819,7 @@ static bool conv_plan(ConvTcParams& p, int CoutL, int Cout, int P_in, int P_out,
                 for (int g = want_stage ? 1 : 0; g >= 0 && !found; --g)
                     if (stages_of(t, w, g) >= (t ? 3 : 2)) { txm = t; wres = w; stage = g; found = true; }
         if (!found) return false;
-        p.txm = txm; p.wres = wres; p.stage_out = stage;
+        p.txm = txm; p.wres = wres; p.stage_out = stage; p.stage_bufs = nbufs;
         p.pair = pair && !wres && (!chan_sums || stage);      // statistics: only the staged epilogue's (no template flag) in pair mode
         if (pair && !p.pair) {                      // planned with half weight tiles but the pair was dropped: plan again without it
             ConvTcParams q = p; q.m_tiles = 1;      // (an odd tile count switches the pair off)
@@ -958,7 +963,7 @@ extern "C" int hd_conv_tc(const void* in0, int C0, const void* in1, int C1, int 
         uint32_t box[2] = {64, (uint32_t)(p.pair ? p.NT / 2 : p.NT)};
         rc = hd_make_tmap_bf16(&mB, w, 2, dims, str, box); if (rc) return rc;
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + (p.stage_out ? 2 * kABytes : 0) + (p.wres ? (size_t)CoutL * p.kb_w * 128 : 0) + 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 2 * 256 * 4 + 2 * 512 * 4;
+    const size_t smem = (size_t)p.stages * stage_bytes + (p.stage_out ? p.stage_bufs * kABytes : 0) + (p.wres ? (size_t)CoutL * p.kb_w * 128 : 0) + 1024 /*align slack*/ + (2 * kMaxStages + 8) * 8 + 2 * 256 * 4 + 2 * 512 * 4;
     static unsigned long long attr_set = 0;
     if (!hd_seen_on_device(&attr_set)) {
         if (cudaFuncSetAttribute(conv_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
