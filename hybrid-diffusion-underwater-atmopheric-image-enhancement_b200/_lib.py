@@ -61,6 +61,7 @@ PROTOTYPES = {
     "hd_sq_err_u8": [P, P, I, L, P, P],
     "hd_uiqm_workspace": [I],
     "hd_uiqm_u8": [P, I, I, I, P, L, P, P],
+    "hd_ssim_u8": [P, P, I, I, I, I, I, P, P],
     "hd_rgb2lab_u8": [P, L, P, P],
     "hd_lab_tables_host": [P, P],
     "hd_uciqe_workspace": [I],

@@ -8,6 +8,7 @@
 //     Python loops and sorts in the reference.  For 8-bit input R - G is an integer and (R + G) / 2 - B a half-integer, so the
 //     alpha-trimmed means come EXACTLY out of two histograms (no sort); Sobel / EME / UIConM are 8 x 8 block reductions;
 //   * hd_rgb2lab_u8: cv2.cvtColor(img, cv2.COLOR_RGB2LAB) for 8-bit images, BIT-EXACT (OpenCV's integer look-up-table path);
+//   * hd_ssim_u8: skimage's structural_similarity as called at utils/rotinas.py:926 (uniform window, exact integer window sums);
 //   * hd_uciqe_u8: UCIQE of metrics/metrics.py:40-76 (chroma deviation, luminance contrast out of a 65536-bin histogram, saturation).
 #include "hd_common.cuh"
 #include <math.h>
@@ -356,6 +357,40 @@ __global__ void uciqe_final_kernel(const UciqeWs* ws, int N, int64_t npix, doubl
     out[4 * n + 1] = var_chr; out[4 * n + 2] = con_lum; out[4 * n + 3] = aver_sat;
 }
 
+// ---- SSIM: skimage.metrics.structural_similarity(a, b, channel_axis=2, data_range=255) as called at utils/rotinas.py:926 (uniform 7 x 7
+// window, sample covariance, K1 = 0.01, K2 = 0.03, borders of (win - 1) / 2 pixels cropped, mean over pixels and channels).  The crop keeps
+// exactly the pixels whose window lies inside the image, so the filter's boundary mode never enters; the five window sums are exact integers
+// for 8-bit input. ----
+__global__ void ssim_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int H, int W, int C, int win, double* out) {
+    __shared__ double red[8];
+    const int n = blockIdx.y, pad = (win - 1) / 2;
+    const int Hi = H - 2 * pad, Wi = W - 2 * pad;
+    const int64_t items = (int64_t)Hi * Wi * C;
+    const uint8_t* pa = a + (int64_t)n * H * W * C;
+    const uint8_t* pb = b + (int64_t)n * H * W * C;
+    const double np_ = (double)(win * win), cov_norm = np_ / (np_ - 1.0);
+    const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C); const int64_t r = i / C;
+        const int x = (int)(r % Wi), y = (int)(r / Wi);            // top-left corner of the window of interior pixel (y + pad, x + pad)
+        int sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+        for (int dy = 0; dy < win; ++dy) {
+            const int64_t row = ((int64_t)(y + dy) * W + x) * C + c;
+            for (int dx = 0; dx < win; ++dx) {
+                const int u = pa[row + (int64_t)dx * C], v = pb[row + (int64_t)dx * C];
+                sx += u; sy += v; sxx += u * u; syy += v * v; sxy += u * v;
+            }
+        }
+        const double ux = sx / np_, uy = sy / np_, uxx = sxx / np_, uyy = syy / np_, uxy = sxy / np_;
+        const double vx = cov_norm * (uxx - ux * ux), vy = cov_norm * (uyy - uy * uy), vxy = cov_norm * (uxy - ux * uy);
+        const double A1 = 2.0 * ux * uy + C1, A2 = 2.0 * vxy + C2, B1 = ux * ux + uy * uy + C1, B2 = vx + vy + C2;
+        acc += (A1 * A2) / (B1 * B2);
+    }
+    const double t = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out + n, t / (double)items);
+}
+
 }  // namespace
 
 extern "C" int hd_resize_bilinear_u8(const void* src, int N, int SH, int SW, int C, void* dst, int DH, int DW, int chw, cudaStream_t stream) {
@@ -424,6 +459,17 @@ extern "C" int hd_uciqe_u8(const void* img, int N, int H, int W, void* workspace
     uciqe_pass_kernel<1><<<dim3(bx, N), 256, 0, stream>>>((const uint8_t*)img, npix, ws);
     uciqe_pass_kernel<2><<<dim3(bx, N), 256, 0, stream>>>((const uint8_t*)img, npix, ws);
     uciqe_final_kernel<<<(N + 63) / 64, 64, 0, stream>>>(ws, N, npix, out);
+    HD_CHECK_LAUNCH();
+    return HD_OK;
+}
+
+// a, b: [N][H][W][C] uint8; out[n] (float64, overwritten) = structural_similarity(a[n], b[n], win_size=win, channel_axis=2, data_range=255)
+extern "C" int hd_ssim_u8(const void* a, const void* b, int N, int H, int W, int C, int win, double* out, cudaStream_t stream) {
+    HD_REQUIRE(a && b && out && N > 0 && C > 0 && win >= 3 && (win & 1) && win <= 15 && H >= win && W >= win);
+    if (cudaMemsetAsync(out, 0, sizeof(double) * N, stream) != cudaSuccess) return HD_ERR_CUDA;
+    const int64_t items = (int64_t)(H - win + 1) * (W - win + 1) * C;
+    int64_t bx = (items + 255) / 256; if (bx > 4 * hd_num_sms()) bx = 4 * hd_num_sms();
+    ssim_u8_kernel<<<dim3((unsigned)bx, N), 256, 0, stream>>>((const uint8_t*)a, (const uint8_t*)b, H, W, C, win, out);
     HD_CHECK_LAUNCH();
     return HD_OK;
 }

@@ -4,6 +4,8 @@ Reference followed (paths relative to the reference repository):
   resize_u8      albumentations A.Resize(256, 256) [= cv2.resize(..., INTER_LINEAR)] + ToTensorV2, utils/utils.py:318-323,441-462
   psnr_u8        skimage.metrics.peak_signal_noise_ratio as imported at utils/rotinas.py:21 (data_range 255)
   uiqm_u8        metrics/metrics.py:77-299 (getUIQM = 0.0282 UICM + 0.2953 UISM + 3.5753 UIConM)
+  ssim_u8        skimage.metrics.structural_similarity(a, b, channel_axis=2, data_range=255) as imported at utils/rotinas.py:22 and called
+                 at :926 (metrics/metrics.py:642 passes win_size=3)
   rgb2lab_u8     cv2.cvtColor(img, cv2.COLOR_RGB2LAB) on 8-bit images, metrics/metrics.py:43
   uciqe_u8       metrics/metrics.py:40-76 (uciqe(nargin=1, loc=img) = 0.4680 var_chr + 0.2745 con_lum + 0.2576 aver_sat)
 All of them call the C-ABI library (csrc/hd_metrics.cu); there is no CPU fallback."""
@@ -72,4 +74,14 @@ def uciqe_u8(images):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=images.device)
     out = torch.empty((N, 4), dtype=torch.float64, device=images.device)
     _lib.check(lib.hd_uciqe_u8(_p(images), N, H, W, _p(ws), nbytes, _p(out), _stream()), "hd_uciqe_u8")
+    return out
+
+
+def ssim_u8(a, b, win_size=7):
+    """SSIM per image of two uint8 batches [N, H, W, C] -> float64 [N] (uniform window, sample covariance, data_range 255, cropped borders)"""
+    assert a.shape == b.shape
+    _check_u8(a, 4); _check_u8(b, 4)
+    N, H, W, C = a.shape
+    out = torch.empty(N, dtype=torch.float64, device=a.device)
+    _lib.check(_lib.load().hd_ssim_u8(_p(a), _p(b), N, H, W, C, int(win_size), _p(out), _stream()), "hd_ssim_u8")
     return out

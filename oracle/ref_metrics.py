@@ -14,6 +14,13 @@ metric kernels of csrc/hd_metrics.cu.
   uciqe_restated       the algorithm of csrc/hd_metrics.cu's UCIQE kernels in numpy float64: per-pixel terms as in the reference,
                        np.histogram(lum, 65536) + cumsum reproduced from a 256-bin integer histogram of L.  Pinned against the
                        reference's own uciqe by tests/test_metrics.py.
+  ssim_restated        scikit-image's structural_similarity for the call the reference makes (utils/rotinas.py:926:
+                       SSIM(res, gt, channel_axis=2, data_range=255); metrics/metrics.py:642 with win_size=3).  PARITY UNPINNED: the algorithm
+                       lives in the third-party dependency scikit-image (reference environment: CLEDiff_bkp.yaml), which is NOT installed in
+                       this image, and the reference holds no golden values for it.  Restated from the published algorithm (Wang et al. 2004
+                       as implemented in skimage/metrics/_structural_similarity.py): float64, scipy.ndimage.uniform_filter (the function
+                       skimage itself calls), sample covariance, K1 = 0.01, K2 = 0.03, borders of (win - 1) // 2 cropped, mean over pixels
+                       per channel, then over channels.
   reference_uciqe      the reference's OWN uciqe (metrics/metrics.py:40-76), cut out of the unmodified file by AST.
   reference_uiqm       the reference's OWN getUIQM (metrics/metrics.py:77-299), cut out of the unmodified file by AST (the module
                        imports torchvision's Inception and skimage at the top and cannot be imported whole here).
@@ -126,6 +133,26 @@ def uciqe_restated(img):
             ihigh = idx
     con_lum = f(ihigh - 1) / f(nb - 1) - f(ilow - 1) / f(nb - 1)
     return 0.4680 * var_chr + 0.2745 * con_lum + 0.2576 * aver_sat, var_chr, con_lum, aver_sat
+
+
+def ssim_restated(im1, im2, win_size=7, data_range=255.0):
+    """im1, im2: HWC uint8 -> float (PARITY UNPINNED, see the module header)"""
+    from scipy.ndimage import uniform_filter
+    k1, k2 = 0.01, 0.03
+    npx = win_size ** 2
+    cov_norm = npx / (npx - 1)
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    pad = (win_size - 1) // 2
+    per_channel = []
+    for ch in range(im1.shape[2]):
+        x, y = im1[..., ch].astype(np.float64), im2[..., ch].astype(np.float64)
+        ux, uy = uniform_filter(x, size=win_size), uniform_filter(y, size=win_size)
+        uxx, uyy, uxy = uniform_filter(x * x, size=win_size), uniform_filter(y * y, size=win_size), uniform_filter(x * y, size=win_size)
+        vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+        a1, a2, b1, b2 = 2 * ux * uy + c1, 2 * vxy + c2, ux ** 2 + uy ** 2 + c1, vx + vy + c2
+        smap = (a1 * a2) / (b1 * b2)
+        per_channel.append(smap[pad:smap.shape[0] - pad, pad:smap.shape[1] - pad].mean(dtype=np.float64))
+    return float(np.mean(per_channel))
 
 
 _cache = {}

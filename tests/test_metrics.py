@@ -147,3 +147,49 @@ def test_uciqe_kernel_vs_reference_uciqe():
         assert np.isclose(got[i, 3], np.mean(chr_ / np.sqrt(chr_ ** 2 + lab[..., 0] ** 2)), rtol=1e-12)
         assert np.isclose(got[i, 1], np.sqrt(np.mean(abs(1 - np.square(np.mean(chr_) / chr_)))), **tol)
         assert np.isclose(got[i, 2], ref_metrics.uciqe_restated(img)[2], rtol=0, atol=1e-15), (i, got[i, 2])     # the histogram bins are exact
+
+
+def _ssim_pairs():
+    rng = np.random.default_rng(7)
+    imgs = _uciqe_images()[:3]
+    noisy = [np.clip(im.astype(np.int64) + rng.integers(-s, s + 1, im.shape), 0, 255).astype(np.uint8) for im, s in zip(imgs, (4, 40, 12))]
+    return list(zip(imgs, noisy)) + [(imgs[0], imgs[0]), (imgs[0], imgs[2])]
+
+
+def test_ssim_restatement_against_the_window_definition():
+    """SSIM has no pinned reference here (scikit-image is absent: parity unpinned); the restatement is at least checked against a direct
+    evaluation of the definition — per interior pixel, plain sums over its win x win window — and on identical images."""
+    for win in (7, 3):
+        for a, b in _ssim_pairs()[:2] + _ssim_pairs()[3:4]:
+            a, b = a[:40, :48], b[:40, :48]
+            pad = (win - 1) // 2
+            tot = []
+            for c in range(3):
+                x, y = a[..., c].astype(np.float64), b[..., c].astype(np.float64)
+                vals = []
+                for i in range(pad, x.shape[0] - pad):
+                    for j in range(pad, x.shape[1] - pad):
+                        wx, wy = x[i - pad:i + pad + 1, j - pad:j + pad + 1], y[i - pad:i + pad + 1, j - pad:j + pad + 1]
+                        ux, uy = wx.mean(), wy.mean()
+                        n = win * win
+                        vx, vy = ((wx - ux) ** 2).sum() / (n - 1), ((wy - uy) ** 2).sum() / (n - 1)
+                        vxy = ((wx - ux) * (wy - uy)).sum() / (n - 1)
+                        c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+                        vals.append((2 * ux * uy + c1) * (2 * vxy + c2) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2)))
+                tot.append(np.mean(vals))
+            assert abs(ref_metrics.ssim_restated(a, b, win) - np.mean(tot)) < 1e-10
+    a = _ssim_pairs()[0][0]
+    assert abs(ref_metrics.ssim_restated(a, a) - 1.0) < 1e-12
+
+
+@pytest.mark.gpu
+def test_ssim_kernel_vs_restatement():
+    from hdiff_b200 import metrics
+    pairs = _ssim_pairs()
+    a = torch.from_numpy(np.stack([p[0] for p in pairs])).cuda()
+    b = torch.from_numpy(np.stack([p[1] for p in pairs])).cuda()
+    for win in (7, 3):
+        got = metrics.ssim_u8(a, b, win_size=win).cpu().numpy()
+        want = [ref_metrics.ssim_restated(p, q, win) for p, q in pairs]
+        assert np.allclose(got, want, rtol=1e-10, atol=1e-12), (win, got, want)
+    assert abs(got[3] - 1.0) < 1e-12
