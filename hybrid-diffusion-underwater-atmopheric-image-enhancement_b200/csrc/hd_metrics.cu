@@ -210,25 +210,26 @@ __global__ void uiqm_final_kernel(const UiqmWs* ws, int N, int H, int W, float* 
 constexpr int kGammaTab = 256, kCbrtTab = 3072, kLabTab = kGammaTab + kCbrtTab;
 __device__ uint16_t g_lab_tab[kLabTab];
 
-static const uint16_t* lab_tables_host() {
-    static uint16_t tab[kLabTab];
-    static bool done = false;                     // idempotent: a second thread computes the same bytes
-    if (!done) {
+struct LabTables {
+    uint16_t v[kLabTab];
+    LabTables() {
         for (int i = 0; i < kGammaTab; ++i) {
             const double x = i / 255.0;
             const double g = x <= 0.04045 ? x / 12.92 : pow((x + 0.055) / 1.055, 2.4);
-            tab[i] = (uint16_t)llrint(255.0 * 8.0 * g);
+            v[i] = (uint16_t)llrint(255.0 * 8.0 * g);
         }
         for (int i = 0; i < kCbrtTab; ++i) {
             const double x = i / (255.0 * 8.0);
             const double f = x < 216.0 / 24389.0 ? x * (841.0 / 108.0) + 16.0 / 116.0 : cbrt(x);
-            tab[kGammaTab + i] = (uint16_t)llrint(32768.0 * f);
+            v[kGammaTab + i] = (uint16_t)llrint(32768.0 * f);
         }
-        tab[kGammaTab + 49] -= 1;
-        tab[kGammaTab + 628] += 1;
-        __atomic_store_n(&done, true, __ATOMIC_RELEASE);
+        v[kGammaTab + 49] -= 1;
+        v[kGammaTab + 628] += 1;
     }
-    return tab;
+};
+static const uint16_t* lab_tables_host() {
+    static const LabTables t;                     // function-local static: initialised once, thread-safe
+    return t.v;
 }
 static int lab_tables_upload(cudaStream_t stream) {
     static unsigned long long seen = 0;
