@@ -112,7 +112,8 @@ int64_t hd_uiqm_workspace(int N);
 int hd_uiqm_u8(const void* img, int N, int H, int W, void* workspace, int64_t ws_bytes, float* out, hd_stream_t stream);
 /*      hd_rgb2lab_u8: cv2.cvtColor(img, cv2.COLOR_RGB2LAB) on 8-bit pixels, bit-exact, [npix][3] -> [npix][3] (metrics/metrics.py:43).
  *      hd_lab_tables_host: the conversion's two look-up tables written to HOST memory (gamma[256], cbrt[3072]); needs no GPU.
- *      hd_uciqe_u8: out[n] = (UCIQE, var_chr, con_lum, aver_sat) in float64 of metrics/metrics.py:40-76 (uciqe(nargin=1, loc=img)). */
+ *      hd_uciqe_u8: out[n] = (UCIQE, var_chr, con_lum, aver_sat) in float64 of metrics/metrics.py:40-76 (uciqe(nargin=1, loc=img)).
+ *      The first hd_rgb2lab_u8 / hd_uciqe_u8 call on a device uploads the tables and synchronises `stream` once (not capturable in a CUDA graph). */
 /*      hd_ssim_u8: out[n] = skimage.metrics.structural_similarity(a[n], b[n], win_size=win, channel_axis=2, data_range=255) in float64
  *      (utils/rotinas.py:22,926; metrics/metrics.py:642 with win = 3). */
 int hd_ssim_u8(const void* a, const void* b, int N, int H, int W, int C, int win, double* out, hd_stream_t stream);
